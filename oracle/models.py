@@ -1,0 +1,210 @@
+"""sympy restatements of the reference's example problems (TEST INFRASTRUCTURE, see oracle/README.md).
+
+Each function returns an oracle.nlp.MPCDef that describes the same optimal-control problem the cited
+reference template files configure.  Only the mathematics is restated; nothing is imported from
+/root/reference.
+
+  cstr_nominal()        examples/CSTR_approximate_mpc/template_model.py:33-105, template_mpc.py:33-91  (BASELINE cfg #2)
+  cstr_robust()         examples/CSTR/template_model.py:33-100,  template_mpc.py:33-110
+  batch_reactor()       examples/batch_reactor/template_model.py:33-75, template_mpc.py:33-86
+  oscillating_masses()  examples/oscillating_masses_discrete/template_model.py:33-75, template_mpc.py:33-70
+  dip()                 examples/double_inverted_pendulum/template_model.py:33-150, template_mpc.py:33-95
+  industrial_poly()     examples/industrial_poly/template_model.py:33-125, template_mpc.py:33-105
+"""
+import itertools
+
+import numpy as np
+import sympy as sy
+
+from .nlp import ModelDef, MPCDef, NlCons
+
+
+def _scenarios(*value_lists):
+    """set_uncertainty_values: all combinations, first = nominal (reference _mpc.py:860-870)."""
+    return np.array(list(itertools.product(*value_lists)), dtype=float)
+
+
+# ------------------------------------------------------------------------------------------------
+def _cstr_model(uncertain):
+    C_a, C_b, T_R, T_K = sy.symbols("C_a C_b T_R T_K")
+    F, Q_dot = sy.symbols("F Q_dot")
+    if uncertain:
+        alpha, beta = sy.symbols("alpha beta")
+        p = [alpha, beta]
+    else:
+        alpha, beta, p = 1, 1, []
+    K0_ab, K0_bc, K0_ad = 1.287e12, 1.287e12, 9.043e9
+    E_A_ab, E_A_bc, E_A_ad = 9758.3, 9758.3, 8560.0
+    H_R_ab, H_R_bc, H_R_ad = 4.2, -11.0, -41.85
+    Rou, Cp, Cp_k, A_R, V_R, m_k, T_in, K_w = 0.9342, 3.01, 2.0, 0.215, 10.01, 5.0, 130.0, 4032.0
+    C_A0 = (5.7 + 4.5) / 2.0
+    T_dif = T_R - T_K
+    K_1 = beta * K0_ab * sy.exp(-E_A_ab / (T_R + 273.15))
+    K_2 = K0_bc * sy.exp(-E_A_bc / (T_R + 273.15))
+    K_3 = K0_ad * sy.exp(-alpha * E_A_ad / (T_R + 273.15))
+    rhs = [
+        F * (C_A0 - C_a) - K_1 * C_a - K_3 * C_a ** 2,
+        -F * C_b + K_1 * C_a - K_2 * C_b,
+        (K_1 * C_a * H_R_ab + K_2 * C_b * H_R_bc + K_3 * C_a ** 2 * H_R_ad) / (-Rou * Cp)
+        + F * (T_in - T_R) + (K_w * A_R * (-T_dif)) / (Rou * Cp * V_R),
+        (Q_dot + K_w * A_R * T_dif) / (m_k * Cp_k),
+    ]
+    return ModelDef("continuous", x=[C_a, C_b, T_R, T_K], u=[F, Q_dot], p=p, rhs=rhs, aux={"T_dif": T_dif})
+
+
+def cstr_nominal(n_horizon=20):
+    m = _cstr_model(False)
+    C_a, C_b = m.x[0], m.x[1]
+    cost = (C_b - 0.6) ** 2 + (C_a - 0.7) ** 2
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.005, n_robust=0, collocation_deg=2, collocation_ni=1,
+                  lterm=cost, mterm=cost, rterm_factor=[0.1, 1e-3],
+                  x_scaling=[1, 1, 100, 100], u_scaling=[100, 2000],
+                  x_lb=[0.1, 0.1, 50, 50], x_ub=[2, 2, 140, 140], u_lb=[5, -8500], u_ub=[100, 0.0])
+
+
+def cstr_robust(n_horizon=20, n_robust=1):
+    m = _cstr_model(True)
+    C_b, T_R = m.x[1], m.x[2]
+    cost = (C_b - 0.6) ** 2
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.005, n_robust=n_robust, collocation_deg=2, collocation_ni=1,
+                  lterm=cost, mterm=cost, rterm_factor=[0.1, 1e-3],
+                  x_scaling=[1, 1, 100, 100], u_scaling=[100, 2000],
+                  x_lb=[0.1, 0.1, 50, 50], x_ub=[2, 2, np.inf, 140], u_lb=[5, -8500], u_ub=[100, 0.0],
+                  nl_cons=[NlCons("T_R", T_R, ub=140, soft=True, penalty=1e2)],
+                  p_scenarios=_scenarios([1.0, 1.05, 0.95], [1.0, 1.1, 0.9]))
+
+
+# ------------------------------------------------------------------------------------------------
+def batch_reactor(n_horizon=20, n_robust=0):
+    X_s, S_s, P_s, V_s, inp, Y_x, S_in = sy.symbols("X_s S_s P_s V_s inp Y_x S_in")
+    mu_m, K_m, K_i, v_par, Y_p = 0.02, 0.05, 5.0, 0.004, 1.2
+    mu_S = mu_m * S_s / (K_m + S_s + (S_s ** 2 / K_i))
+    rhs = [mu_S * X_s - inp / V_s * X_s,
+           -mu_S * X_s / Y_x - v_par * X_s / Y_p + inp / V_s * (S_in - S_s),
+           v_par * X_s - inp / V_s * P_s,
+           inp]
+    m = ModelDef("continuous", x=[X_s, S_s, P_s, V_s], u=[inp], p=[Y_x, S_in], rhs=rhs)
+    return MPCDef(m, n_horizon=n_horizon, t_step=1.0, n_robust=n_robust, collocation_deg=2, collocation_ni=2,
+                  lterm=-P_s, mterm=-P_s, rterm_factor=[1.0],
+                  x_lb=[0.0, -0.01, 0.0, 0.0], x_ub=[3.7, np.inf, 3.0, np.inf], u_lb=[0.0], u_ub=[0.2],
+                  p_scenarios=_scenarios([0.5, 0.4, 0.3], [200.0, 220.0, 180.0]))
+
+
+# ------------------------------------------------------------------------------------------------
+def oscillating_masses(n_horizon=7):
+    x = list(sy.symbols("x0:4")); u = [sy.Symbol("u")]
+    A = np.array([[0.763, 0.460, 0.115, 0.020], [-0.899, 0.763, 0.420, 0.115],
+                  [0.115, 0.020, 0.763, 0.460], [0.420, 0.115, -0.899, 0.763]])
+    B = np.array([0.014, 0.063, 0.221, 0.367])
+    rhs = [sum(A[i, j] * x[j] for j in range(4)) + B[i] * u[0] for i in range(4)]
+    cost = sum(xi ** 2 for xi in x)
+    m = ModelDef("discrete", x=x, u=u, rhs=rhs, aux={"cost": cost})
+    mx = np.array([4.0, 10.0, 4.0, 10.0])
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.5, n_robust=0, lterm=cost, mterm=cost, rterm_factor=[1e-4],
+                  x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5])
+
+
+# ------------------------------------------------------------------------------------------------
+def dip(n_horizon=100, obstacles=({"x": 0.0, "y": 0.6, "r": 0.3},)):
+    m0, L1, L2 = 0.6, 0.5, 0.5
+    l1, l2 = L1 / 2, L2 / 2
+    J1 = (0.2 * l1 ** 2) / 3
+    J2 = (0.2 * l2 ** 2) / 3
+    m1, m2 = sy.symbols("m1 m2")
+    g = 9.80665
+    h1 = m0 + m1 + m2
+    h2 = m1 * l1 + m2 * L1
+    h3 = m2 * l2
+    h4 = m1 * l1 ** 2 + m2 * L1 ** 2 + J1
+    h5 = m2 * l2 * L1
+    h6 = m2 * l2 ** 2 + J2
+    h7 = (m1 * l1 + m2 * L1) * g
+    h8 = m2 * l2 * g
+    pos_set = sy.Symbol("pos_set")
+    pos, th0, th1, dpos, dth0, dth1 = sy.symbols("pos th0 th1 dpos dth0 dth1")
+    ddpos, ddth0, ddth1 = sy.symbols("ddpos ddth0 ddth1")
+    u = sy.Symbol("force")
+    rhs = [dpos, dth0, dth1, ddpos, ddth0, ddth1]
+    alg = [
+        h1 * ddpos + h2 * ddth0 * sy.cos(th0) + h3 * ddth1 * sy.cos(th1)
+        - (h2 * dth0 ** 2 * sy.sin(th0) + h3 * dth1 ** 2 * sy.sin(th1) + u),
+        h2 * sy.cos(th0) * ddpos + h4 * ddth0 + h5 * sy.cos(th0 - th1) * ddth1
+        - (h7 * sy.sin(th0) - h5 * dth1 ** 2 * sy.sin(th0 - th1)),
+        h3 * sy.cos(th1) * ddpos + h5 * sy.cos(th0 - th1) * ddth0 + h6 * ddth1
+        - (h5 * dth0 ** 2 * sy.sin(th0 - th1) + h8 * sy.sin(th1)),
+    ]
+    half = sy.Rational(1, 2)
+    E_kin_cart = half * m0 * dpos ** 2
+    E_kin_p1 = half * m1 * ((dpos + l1 * dth0 * sy.cos(th0)) ** 2 + (l1 * dth0 * sy.sin(th0)) ** 2) + half * J1 * dth0 ** 2
+    E_kin_p2 = half * m2 * ((dpos + L1 * dth0 * sy.cos(th0) + l2 * dth1 * sy.cos(th1)) ** 2
+                            + (L1 * dth0 * sy.sin(th0) + l2 * dth1 * sy.sin(th1)) ** 2) + half * J2 * dth0 ** 2
+    E_kin = E_kin_cart + E_kin_p1 + E_kin_p2
+    E_pot = m1 * g * l1 * sy.cos(th0) + m2 * g * (L1 * sy.cos(th0) + l2 * sy.cos(th1))
+    n0x, n0y = pos, 0
+    n1x, n1y = n0x + L1 * sy.sin(th0), n0y + L1 * sy.cos(th0)
+    n2x, n2y = n1x + L2 * sy.sin(th1), n1y + L2 * sy.cos(th1)
+    dist = []
+    for ob in obstacles:
+        for (nx_, ny_) in ((n0x, n0y), (n1x, n1y), (n2x, n2y)):
+            dist.append(sy.sqrt((nx_ - ob["x"]) ** 2 + (ny_ - ob["y"]) ** 2) - ob["r"] * 1.05)
+    aux = {"E_kin": E_kin, "E_pot": E_pot}
+    for i, d_ in enumerate(dist):
+        aux[f"obstacle_distance_{i}"] = d_
+    aux["tvp"] = pos_set
+    m = ModelDef("continuous", x=[pos, th0, th1, dpos, dth0, dth1], u=[u], z=[ddpos, ddth0, ddth1],
+                 tvp=[pos_set], p=[m1, m2], rhs=rhs, alg=alg, aux=aux)
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.04, n_robust=0, collocation_deg=3, collocation_ni=1,
+                  lterm=-E_pot + 10 * (pos - pos_set) ** 2, mterm=E_kin - E_pot, rterm_factor=[0.1],
+                  u_lb=[-4], u_ub=[4],
+                  nl_cons=[NlCons(f"obstacles_{i}", -d_, ub=0.0) for i, d_ in enumerate(dist)],
+                  p_scenarios=_scenarios(0.2 * np.array([1, 0.95, 1.05]), 0.2 * np.array([1, 0.95, 1.05])))
+
+
+# ------------------------------------------------------------------------------------------------
+def industrial_poly(n_horizon=20, n_robust=1):
+    R, T_F, E_a, A_tank = 8.314, 25 + 273.15, 8500.0, 65.0
+    k_U2, k_U1, w_WF, w_AF = 32.0, 4.0, .333, .667
+    m_M_KW, fm_M_KW, m_AWT_KW, fm_AWT_KW, m_AWT, fm_AWT, m_S = 5000.0, 300000.0, 1000.0, 100000.0, 200.0, 20000.0, 39000.0
+    c_pW, c_pS, c_pF, c_pR = 4.2, .47, 3.0, 5.0
+    k_WS, k_AS, k_PS = 17280.0, 3600.0, 360.0
+    alfa = 5 * 20e4 * 3.6
+    p_1 = 1.0
+    m_W, m_A, m_P, T_R, T_S, Tout_M, T_EK, Tout_AWT, accum_monom, T_adiab = sy.symbols(
+        "m_W m_A m_P T_R T_S Tout_M T_EK Tout_AWT accum_monom T_adiab")
+    m_dot_f, T_in_M, T_in_EK = sy.symbols("m_dot_f T_in_M T_in_EK")
+    delH_R, k_0 = sy.symbols("delH_R k_0")
+    U_m = m_P / (m_A + m_P)
+    m_ges = m_W + m_A + m_P
+    k_R1 = k_0 * sy.exp(-E_a / (R * T_R)) * ((k_U1 * (1 - U_m)) + (k_U2 * U_m))
+    k_R2 = k_0 * sy.exp(-E_a / (R * T_EK)) * ((k_U1 * (1 - U_m)) + (k_U2 * U_m))
+    k_K = ((m_W / m_ges) * k_WS) + ((m_A / m_ges) * k_AS) + ((m_P / m_ges) * k_PS)
+    dot_m_W = m_dot_f * w_WF
+    react = k_R1 * (m_A - ((m_A * m_AWT) / (m_W + m_A + m_P)))
+    ehe = p_1 * k_R2 * (m_A / m_ges) * m_AWT
+    dot_m_A = (m_dot_f * w_AF) - react - ehe
+    dot_m_P = react + ehe
+    dot_T_R = 1. / (c_pR * m_ges) * ((m_dot_f * c_pF * (T_F - T_R)) - (k_K * A_tank * (T_R - T_S))
+                                     - (fm_AWT * c_pR * (T_R - T_EK)) + (delH_R * react))
+    rhs = [
+        dot_m_W, dot_m_A, dot_m_P, dot_T_R,
+        1. / (c_pS * m_S) * ((k_K * A_tank * (T_R - T_S)) - (k_K * A_tank * (T_S - Tout_M))),
+        1. / (c_pW * m_M_KW) * ((fm_M_KW * c_pW * (T_in_M - Tout_M)) + (k_K * A_tank * (T_S - Tout_M))),
+        1. / (c_pR * m_AWT) * ((fm_AWT * c_pR * (T_R - T_EK)) - (alfa * (T_EK - Tout_AWT)) + (ehe * delH_R)),
+        1. / (c_pW * m_AWT_KW) * ((fm_AWT_KW * c_pW * (T_in_EK - Tout_AWT)) - (alfa * (Tout_AWT - T_EK))),
+        m_dot_f,
+        delH_R / (m_ges * c_pR) * dot_m_A - (dot_m_A + dot_m_W + dot_m_P) * (m_A * delH_R / (m_ges * m_ges * c_pR)) + dot_T_R,
+    ]
+    m = ModelDef("continuous", x=[m_W, m_A, m_P, T_R, T_S, Tout_M, T_EK, Tout_AWT, accum_monom, T_adiab],
+                 u=[m_dot_f, T_in_M, T_in_EK], p=[delH_R, k_0], rhs=rhs)
+    tr = 2.0
+    inf = np.inf
+    nl = []
+    x_ub = [inf, inf, inf, 363.15 + tr, 400.0, 400.0, 400.0, 400.0, 30000.0, 382.15]
+    if n_robust == 0:
+        nl = [NlCons("T_R_UB", T_R, ub=363.15 + tr, soft=True, penalty=1e4)]
+    return MPCDef(m, n_horizon=n_horizon, t_step=50.0 / 3600.0, n_robust=n_robust, collocation_deg=2, collocation_ni=1,
+                  lterm=-m_P, mterm=-m_P, rterm_factor=[0.002, 0.004, 0.002],
+                  x_scaling=[10, 10, 10, 1, 1, 1, 1, 1, 10, 1], u_scaling=[100, 1, 1],
+                  x_lb=[0.0, 0.0, 26.0, 363.15 - tr, 298.0, 298.0, 288.0, 288.0, 0.0, -inf], x_ub=x_ub,
+                  u_lb=[0.0, 333.15, 333.15], u_ub=[3.0e4, 373.15, 373.15], nl_cons=nl,
+                  p_scenarios=_scenarios([950.0, 950.0 * 1.30, 950.0 * 0.70], [7.0, 7.0 * 1.30, 7.0 * 0.70]))
