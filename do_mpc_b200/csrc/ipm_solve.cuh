@@ -1,0 +1,414 @@
+// Interior-point driver for one instance (all threads of a CTA cooperate).  See ipm_core.cuh.
+// Algorithm and constants: Waechter & Biegler (2006), IPOPT defaults — identical to oracle/ipm.py.
+#pragma once
+#include "ipm_core.cuh"
+
+struct DmbShared {          // small per-CTA state in shared memory
+  double red[40];           // reduction scratch
+  double filt_theta[MAX_FILTER], filt_phi[MAX_FILTER];
+  int n_filt;
+  int flag, fail;
+};
+
+struct DmbResult {
+  double f, mu, inf_pr, inf_du, df;
+  int status, iters, n_resto;
+};
+
+DMB_DEV double ftb_step(double slack, double dslack, double tau) {   // largest a: slack + a*dslack >= (1-tau)*slack
+  return dslack < 0.0 ? -tau * slack / dslack : 1.0;
+}
+
+// barrier function value given objective f (scaled); returns +inf outside the bounds
+DMB_DEV double barrier_phi(const Ctx& c, const Inst& I, const double* w, const double* s, double mu, double kappa_d,
+                           double f, double* red) {
+  double acc = 0.0; double bad = 0.0;
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
+    if (hl) { const double sl = w[i] - I.lb[i]; if (sl <= 0.0) bad = 1.0; else { acc -= mu * log(sl); if (!hu) acc += kappa_d * mu * sl; } }
+    if (hu) { const double su = I.ub[i] - w[i]; if (su <= 0.0) bad = 1.0; else { acc -= mu * log(su); if (!hl) acc += kappa_d * mu * su; } }
+  }
+#if NNL > 0
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - s[i];
+    if (su <= 0.0) bad = 1.0; else acc += -mu * log(su) + kappa_d * mu * su;
+  }
+#endif
+  const double b = block_max(c, bad, red);
+  const double a = block_sum(c, acc, red);
+  return b > 0.0 ? INFINITY : f + a;
+}
+
+// optimality error pieces for a given mu: dual infeasibility uses gl = grad L (without z), then -zL+zU
+DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, double* red,
+                       double* dual, double* compl_, double* s_d, double* s_c) {
+  double du = 0.0, cm = 0.0, sz = 0.0, nz = 0.0, sy = 0.0;
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
+    double r = I.gl[i];
+    if (hl) { r -= I.zL[i]; cm = fmax(cm, fabs((I.w[i] - I.lb[i]) * I.zL[i] - mu)); sz += fabs(I.zL[i]); nz += 1.0; }
+    if (hu) { r += I.zU[i]; cm = fmax(cm, fabs((I.ub[i] - I.w[i]) * I.zU[i] - mu)); sz += fabs(I.zU[i]); nz += 1.0; }
+    du = fmax(du, fabs(r));
+  }
+#if NNL > 0
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    const int e = i / NNL, j = i % NNL;
+    const double yd = I.lam[LAM_EDGE(e) + NY + NX + j];
+    du = fmax(du, fabs(-yd + I.vU[i]));
+    cm = fmax(cm, fabs((nl_ub_relaxed(I, e, j) - I.s[i]) * I.vU[i] - mu));
+    sz += fabs(I.vU[i]); nz += 1.0;
+  }
+#endif
+  for (int i = c.tid; i < NLAM; i += c.nthr) sy += fabs(I.lam[i]);
+  *dual = block_max(c, du, red);
+  *compl_ = block_max(c, cm, red);
+  const double SZ = block_sum(c, sz, red), NZ = block_sum(c, nz, red), SY = block_sum(c, sy, red);
+  const double m_tot = (double)NLAM_ACTIVE;
+  *s_d = fmax(s_max, (SY + SZ) / fmax(m_tot + NZ, 1.0)) / s_max;
+  *s_c = fmax(s_max, SZ / fmax(NZ, 1.0)) / s_max;
+}
+
+// full structured solve: edges already factorised for the current point
+DMB_DEV void direction(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, double delta, int ls_mode,
+                       int recompute_y0, double* Qs, DmbShared* S) {
+  solve_edges(c, I, res, delta, recompute_y0);
+  riccati_backward(c, I, mu, kappa_d, delta, ls_mode, Qs, &S->flag);
+}
+
+DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o, const double* x0_internal,
+                            double* tile, double* hq, double* Qs, DmbShared* S, DmbResult* out) {
+  Inst I = I_in;
+  double* red = S->red;
+  // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
+  for (int i = c.tid; i < NWI; i += c.nthr) { I.w[i] = x0_internal[i]; I.zL[i] = 0.0; I.zU[i] = 0.0; }
+  for (int i = c.tid; i < NLAM; i += c.nthr) { I.dc[i] = 1.0; I.lam[i] = 0.0; }
+  I.df = 1.0;
+  CTA_SYNC();
+  eval_gradient(c, I, I.w, I.lam, 0, I.gl);
+  {
+    double g = 0.0;
+    for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.gl[i]));
+    g = block_max(c, g, red);
+    if (g > o.nlp_scaling_max_gradient) I.df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
+  }
+  for (int e = c.tid; e < NEDGE; e += c.nthr) {
+    double q[NQ], jnz[DMB_NNZ_J > 0 ? DMB_NNZ_J : 1], mx[NY > 0 ? NY : 1];
+    gather_q(I.w, e, q);
+    gen_J(q, edge_tvp(I.p, e), edge_pp(I.p, e), jnz);
+    for (int i = 0; i < NY; ++i) mx[i] = 0.0;
+    for (int k = 0; k < DMB_NNZ_J; ++k) mx[DMB_J_ROW[k]] = fmax(mx[DMB_J_ROW[k]], fabs(jnz[k]));
+    for (int i = 0; i < NY; ++i)
+      I.dc[LAM_EDGE(e) + i] = mx[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / mx[i], o.nlp_scaling_min_value) : 1.0;
+#if NNL > 0
+    double dnz[DMB_NNZ_D > 0 ? DMB_NNZ_D : 1], md[NNL];
+    gen_nl_jac(q, edge_tvp(I.p, e), edge_pp(I.p, e), dnz);
+    for (int i = 0; i < NNL; ++i) md[i] = 0.0;
+    for (int k = 0; k < DMB_NNZ_D; ++k) md[DMB_D_ROW[k]] = fmax(md[DMB_D_ROW[k]], fabs(dnz[k]));
+    for (int i = 0; i < NNL; ++i)
+      I.dc[LAM_EDGE(e) + NY + NX + i] = md[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / md[i], o.nlp_scaling_min_value) : 1.0;
+#endif
+  }
+  CTA_SYNC();
+  // ---- starting point: push into the (relaxed) bounds, slacks, bound multipliers ----------------------------
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const double lo = I.lb[i], hi = I.ub[i];
+    const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
+    double v = I.w[i];
+    if (hl && hu) {
+      const double pl = fmin(o.bound_push * fmax(1.0, fabs(lo)), o.bound_frac * (hi - lo));
+      const double pu = fmin(o.bound_push * fmax(1.0, fabs(hi)), o.bound_frac * (hi - lo));
+      v = fmin(fmax(v, lo + pl), hi - pu);
+    } else if (hl) v = fmax(v, lo + o.bound_push * fmax(1.0, fabs(lo)));
+    else if (hu) v = fmin(v, hi - o.bound_push * fmax(1.0, fabs(hi)));
+    I.w[i] = v;
+    I.zL[i] = hl ? o.bound_mult_init_val : 0.0;
+    I.zU[i] = hu ? o.bound_mult_init_val : 0.0;
+  }
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) { I.s[i] = 0.0; I.vU[i] = o.bound_mult_init_val; }
+  CTA_SYNC();
+  double f, theta, inf_pr;
+  eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
+#if NNL > 0
+  // slack init: s = d(x) pushed below the (relaxed) upper bound; residual d - s follows
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    const int e = i / NNL, j = i % NNL;
+    const double d = I.res[LAM_EDGE(e) + NY + NX + j];      // s was 0
+    const double hi = nl_ub_relaxed(I, e, j);
+    I.s[i] = fmin(d, hi - o.bound_push * fmax(1.0, fabs(hi)));
+  }
+  CTA_SYNC();
+  eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
+#endif
+  // ---- least-squares multiplier estimate ----------------------------------------------------------------------------
+  if (c.tid == 0) { S->fail = 0; S->n_filt = 0; }
+  CTA_SYNC();
+  factor_edges(c, I, 0.0, 0.0, 1, tile, hq, &S->fail);
+  CTA_SYNC();
+  for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = 0.0;
+  CTA_SYNC();
+  direction(c, I, I.rest, 0.0, 0.0, 0.0, 1, 1, Qs, S);
+  forward_recover(c, I, I.rest, 0.0);
+  {
+    double m = 0.0;
+    for (int i = c.tid; i < NLAM; i += c.nthr) m = fmax(m, fabs(I.lamn[i]));
+    m = block_max(c, m, red);
+    const bool ok = (m <= o.constr_mult_init_max) && !S->flag && !S->fail && (m == m);
+    for (int i = c.tid; i < NLAM; i += c.nthr) I.lam[i] = ok ? I.lamn[i] : 0.0;
+  }
+  CTA_SYNC();
+
+  double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
+  const double theta_max = o.theta_max_fact * fmax(1.0, theta), theta_min = o.theta_min_fact * fmax(1.0, theta);
+  double delta_w_last = 0.0;
+  int it = 0, status = DMB_MAXIMUM_ITERATIONS_EXCEEDED, acceptable_cnt = 0, n_resto = 0;
+  const int degenerate_reg = o.mimic_dummy_reg && DMB_HAS_DUMMIES;
+  double dual0 = 0.0;
+
+  while (true) {
+    // ---- convergence tests ----------------------------------------------------------------------------------------------
+    eval_gradient(c, I, I.w, I.lam, 1, I.gl);
+    double dual, cmpl, s_d, s_c;
+    kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
+    dual0 = dual;
+    const double E0 = fmax(fmax(dual / s_d, inf_pr), cmpl / s_c);
+    {
+      // unscaled secondary tolerances
+      double pu = 0.0;
+      for (int i = c.tid; i < NLAM; i += c.nthr) pu = fmax(pu, fabs(I.res[i]) / I.dc[i]);
+      pu = block_max(c, pu, red);
+      const double du_u = dual / I.df, cm_u = cmpl / I.df;
+      if (!(E0 == E0)) { status = DMB_INVALID_NUMBER_DETECTED; break; }
+      if (E0 <= o.tol && du_u <= o.dual_inf_tol && pu <= o.constr_viol_tol && cm_u <= o.compl_inf_tol) { status = DMB_SOLVE_SUCCEEDED; break; }
+      if (E0 <= o.acceptable_tol && du_u <= o.acceptable_dual_inf_tol && pu <= o.acceptable_constr_viol_tol && cm_u <= o.acceptable_compl_inf_tol) {
+        if (++acceptable_cnt >= o.acceptable_iter) { status = DMB_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
+      } else acceptable_cnt = 0;
+      if (it >= o.max_iter) { status = DMB_MAXIMUM_ITERATIONS_EXCEEDED; break; }
+    }
+    // ---- barrier parameter (monotone, repeated decrease allowed) ----------------------------------------------------
+    while (true) {
+      double dm, cmm, sd2, sc2;
+      kkt_error(c, I, mu, o.s_max, red, &dm, &cmm, &sd2, &sc2);
+      const double Emu = fmax(fmax(dm / sd2, inf_pr), cmm / sc2);
+      if (Emu <= o.kappa_eps * mu && mu > o.mu_min) {
+        double nm = fmax(o.tol / 10.0, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+        nm = fmax(nm, o.mu_min);
+        if (nm >= mu) break;
+        mu = nm; tau = fmax(o.tau_min, 1.0 - mu);
+        if (c.tid == 0) S->n_filt = 0;
+        CTA_SYNC();
+      } else break;
+    }
+    // ---- search direction ------------------------------------------------------------------------------------------------
+    if (c.tid == 0) S->fail = 0;
+    CTA_SYNC();
+    factor_edges(c, I, mu, o.kappa_d, 0, tile, hq, &S->fail);
+    CTA_SYNC();
+    double delta_w = 0.0;
+    if (degenerate_reg) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
+    bool step_fail = S->fail != 0;
+    while (!step_fail) {
+      direction(c, I, I.res, mu, o.kappa_d, delta_w, 0, 0, Qs, S);
+      if (!S->flag) break;
+      if (delta_w == 0.0) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
+      else delta_w *= (delta_w_last == 0.0 ? o.kappa_w_plus_first : o.kappa_w_plus);
+      if (delta_w > o.delta_w_max) step_fail = true;
+    }
+    if (step_fail) { status = DMB_ERROR_IN_STEP_COMPUTATION; break; }
+    if (delta_w > 0.0) delta_w_last = delta_w;
+    forward_recover(c, I, I.res, delta_w);
+
+    // ---- step sizes, directional derivative ----------------------------------------------------------------------------
+    eval_gradient(c, I, I.w, I.lam, 0, I.gl);            // objective gradient (scaled by df)
+    double a_max = 1.0, a_z = 1.0, dphi = 0.0;
+    for (int i = c.tid; i < NWI; i += c.nthr) {
+      const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
+      double g = I.gl[i];
+      const double d = I.dw[i];
+      if (hl) {
+        const double sl = I.w[i] - I.lb[i];
+        a_max = fmin(a_max, ftb_step(sl, d, tau));
+        const double dz = mu / sl - I.zL[i] - I.zL[i] / sl * d;
+        a_z = fmin(a_z, ftb_step(I.zL[i], dz, tau));
+        g -= mu / sl; if (!hu) g += o.kappa_d * mu;
+      }
+      if (hu) {
+        const double su = I.ub[i] - I.w[i];
+        a_max = fmin(a_max, ftb_step(su, -d, tau));
+        const double dz = mu / su - I.zU[i] + I.zU[i] / su * d;
+        a_z = fmin(a_z, ftb_step(I.zU[i], dz, tau));
+        g += mu / su; if (!hl) g -= o.kappa_d * mu;
+      }
+      dphi += g * d;
+    }
+#if NNL > 0
+    for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+      const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - I.s[i];
+      const double d = I.ds[i];
+      a_max = fmin(a_max, ftb_step(su, -d, tau));
+      const double dv = mu / su - I.vU[i] + I.vU[i] / su * d;
+      a_z = fmin(a_z, ftb_step(I.vU[i], dv, tau));
+      dphi += (mu / su - o.kappa_d * mu) * d;
+    }
+#endif
+    a_max = block_min(c, a_max, red);
+    a_z = block_min(c, a_z, red);
+    dphi = block_sum(c, dphi, red);
+    const double phi = barrier_phi(c, I, I.w, I.s, mu, o.kappa_d, f, red);
+
+    // ---- filter line search -------------------------------------------------------------------------------------------------
+    double a_min;
+    if (dphi < 0.0 && theta <= theta_min)
+      a_min = fmin(fmin(o.gamma_theta, o.gamma_phi * theta / (-dphi)), o.delta * pow(theta, o.s_theta) / pow(-dphi, o.s_phi));
+    else if (dphi < 0.0) a_min = fmin(o.gamma_theta, o.gamma_phi * theta / (-dphi));
+    else a_min = o.gamma_theta;
+    a_min *= o.alpha_min_frac;
+    double alpha = a_max, a_used = a_max;
+    bool accepted = false, armijo = false;
+    double f_t = f, theta_t = theta, infpr_t = inf_pr;
+    const double eps_r = 10.0 * 2.220446049250313e-16;
+    int ls = 0;
+    while (alpha >= a_min || ls == 0) {
+      ++ls;
+      for (int i = c.tid; i < NWI; i += c.nthr) I.wt[i] = I.w[i] + alpha * I.dw[i];
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.s[i] + alpha * I.ds[i];
+      CTA_SYNC();
+      eval_point(c, I, I.wt, I.st, I.rest, red, &f_t, &theta_t, &infpr_t);
+      const double phi_t = barrier_phi(c, I, I.wt, I.st, mu, o.kappa_d, f_t, red);
+      bool ok = false, arm = false;
+      if (phi_t == phi_t && phi_t < INFINITY && theta_t <= theta_max) {
+        const bool switching = (dphi < 0.0) && (alpha * pow(-dphi, o.s_phi) > o.delta * pow(theta, o.s_theta));
+        if (theta <= theta_min && switching) {
+          ok = (phi_t - phi - eps_r * fabs(phi) <= o.eta_phi * alpha * dphi); arm = true;
+        } else {
+          ok = (theta_t - (1.0 - o.gamma_theta) * theta <= eps_r * fabs(theta)) ||
+               (phi_t - (phi - o.gamma_phi * theta) <= eps_r * fabs(phi));
+        }
+        if (ok) for (int k = 0; k < S->n_filt; ++k) if (!(theta_t < S->filt_theta[k] || phi_t < S->filt_phi[k])) { ok = false; break; }
+      }
+      if (ok) { accepted = true; armijo = arm; a_used = alpha; break; }
+      // TODO(second-order correction): the oracle applies it on the first trial when theta grows; see DESIGN.md
+      alpha *= o.alpha_red_factor;
+    }
+    if (!accepted) {
+      // restoration substitute is not implemented on the device: report like the oracle does when it fails
+      ++n_resto;
+      status = theta > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED;
+      break;
+    }
+    // ---- accept ------------------------------------------------------------------------------------------------------------------
+    if (!armijo && c.tid == 0) {
+      int k = S->n_filt < MAX_FILTER ? S->n_filt++ : MAX_FILTER - 1;
+      S->filt_theta[k] = (1.0 - o.gamma_theta) * theta; S->filt_phi[k] = phi - o.gamma_phi * theta;
+    }
+    for (int i = c.tid; i < NWI; i += c.nthr) {
+      const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
+      const double d = I.dw[i], wn = I.wt[i];
+      if (hl) {
+        const double sl = I.w[i] - I.lb[i];
+        double z = I.zL[i] + a_z * (mu / sl - I.zL[i] - I.zL[i] / sl * d);
+        const double sn = wn - I.lb[i];
+        z = fmax(fmin(z, o.kappa_sigma * mu / sn), mu / (o.kappa_sigma * sn));
+        I.zL[i] = z;
+      }
+      if (hu) {
+        const double su = I.ub[i] - I.w[i];
+        double z = I.zU[i] + a_z * (mu / su - I.zU[i] + I.zU[i] / su * d);
+        const double sn = I.ub[i] - wn;
+        z = fmax(fmin(z, o.kappa_sigma * mu / sn), mu / (o.kappa_sigma * sn));
+        I.zU[i] = z;
+      }
+      I.w[i] = wn;
+    }
+#if NNL > 0
+    for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+      const double hi = nl_ub_relaxed(I, i / NNL, i % NNL);
+      const double su = hi - I.s[i];
+      double v = I.vU[i] + a_z * (mu / su - I.vU[i] + I.vU[i] / su * I.ds[i]);
+      const double sn = hi - I.st[i];
+      v = fmax(fmin(v, o.kappa_sigma * mu / sn), mu / (o.kappa_sigma * sn));
+      I.vU[i] = v; I.s[i] = I.st[i];
+    }
+#endif
+    for (int i = c.tid; i < NLAM; i += c.nthr) { I.lam[i] += a_used * (I.lamn[i] - I.lam[i]); I.res[i] = I.rest[i]; }
+    f = f_t; theta = theta_t; inf_pr = infpr_t;
+    CTA_SYNC();
+    ++it;
+  }
+  if (c.tid == 0) {
+    out->f = f / I.df; out->mu = mu; out->inf_pr = inf_pr; out->inf_du = dual0;
+    out->status = status; out->iters = it; out->n_resto = n_resto; out->df = I.df;
+  }
+  CTA_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// instance I/O in the reference's flat layouts
+// ---------------------------------------------------------------------------------------------------
+// initial guess -> internal layout (into dst).  Either a flat opt_x vector (scaled variables), or the
+// broadcast of (x0, u0, z0) that MPC.set_initial_guess performs (reference _mpc.py:969-971).
+DMB_DEV void load_initial_guess(const Ctx& c, const double* x_flat, const double* x0s, const double* u0s,
+                                const double* z0s, double* dst) {
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    double v = 0.0;
+    const int fl = DMB_W2FLAT[i];
+    if (x_flat) {
+      if (fl >= 0) v = x_flat[fl];
+      else if (i >= NNODE * NVP) {
+        // auxiliary end-of-interval state of a discrete edge: start from the child's node state
+        const int e = (i - NNODE * NVP) / NY, j = (i - NNODE * NVP) % NY;
+        v = x_flat[DMB_NODE_X_FLAT[DMB_EDGE_CHILD[e]] + (j - DMB_NZ)];
+      }
+    } else {
+      if (i < NNODE * NVP) {
+        const int j = i % NVP;
+        if (j < NX) v = x0s[j]; else if (j < NX + NU) v = u0s[j - NX];
+      } else {
+        const int j = (i - NNODE * NVP) % NY;
+#if DMB_DISCRETE
+        v = j < DMB_NZ ? z0s[j] : x0s[j - DMB_NZ];
+#else
+        v = j < DMB_NPC * NX ? x0s[j % NX] : z0s[(j - DMB_NPC * NX) % (DMB_NZ > 0 ? DMB_NZ : 1)];
+#endif
+      }
+    }
+    dst[i] = v;
+  }
+  CTA_SYNC();
+}
+
+// solution -> flat arrays.  x_out must already hold the initial guess (unused reference variables keep it).
+DMB_DEV void store_solution(const Ctx& c, const Inst& I, double df, double* x_out, double* lam_g_out, double* lam_x_out,
+                            double* g_out) {
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const int fl = DMB_W2FLAT[i];
+    if (fl < 0) continue;
+    if (x_out) x_out[fl] = I.w[i];
+    if (lam_x_out) {
+      double l = 0.0;
+      if (I.lb[i] > -DMB_INF) l -= I.zL[i];
+      if (I.ub[i] < DMB_INF) l += I.zU[i];
+      lam_x_out[fl] = l / df;
+    }
+  }
+  for (int i = c.tid; i < NLAM; i += c.nthr) {
+    const int fl = DMB_LAM2FLAT[i];
+    if (fl < 0) continue;
+    if (lam_g_out) lam_g_out[fl] = I.dc[i] * I.lam[i] / df;
+    if (g_out) {
+      double r = I.res[i];
+#if NNL > 0
+      if (i >= NX) { const int j = (i - NX) % NLE; if (j >= NY + NX) r += I.s[((i - NX) / NLE) * NNL + (j - NY - NX)]; }
+#endif
+      g_out[fl] = r / I.dc[i];
+    }
+  }
+  CTA_SYNC();
+}
+
+DMB_DEV void bind_instance(Inst& I, double* vec, double* ws_edge_node) {
+  I.w = vec + WV_W; I.wt = vec + WV_WT; I.dw = vec + WV_DW; I.zL = vec + WV_ZL; I.zU = vec + WV_ZU;
+  I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
+  I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU; I.gl = vec + WV_GL;
+  I.edge = ws_edge_node; I.node = ws_edge_node + (size_t)NEDGE * WS_EDGE;
+}
+#define DMB_QS_SIZE (NV * NV + NV + 2 * NXI * NV)

@@ -1,0 +1,251 @@
+"""Stage-structured NLP recipe: what MPC.setup() hands to the CUDA code generator.
+
+The reference builds one flat symbolic NLP (do_mpc/controller/_mpc.py:1097-1301) and lets CasADi
+differentiate all n_w variables.  Because that NLP is stage-repetitive, this package instead keeps
+  * the per-stage atoms as small expression graphs in *scaled* stage symbols, and
+  * integer tables describing the scenario tree (do_mpc/optimizer.py:998-1048) and the flat
+    opt_x / opt_p / g layouts,
+and generates kernels that evaluate every (instance, edge) with the same code.
+
+Vocabulary: a *node* is (k, s) — the state `_x[k, s, -1]` with its input `_u[k, s]` and slack `_eps[k, s]`;
+an *edge* is (k, s, b) — one discretised interval from node (k, s) to child node (k+1, child[k][s][b]),
+owning the collocation unknowns y = [_x[k+1, ch, 0..P-1] | _z[k, ch, 0..Pz-1]].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+from .sym import expr as E
+from .sym.sx import SX, Function, collocation_points, vertcat
+
+
+def collocation_constants(deg: int, scheme: str):
+    """tau_root, C, D exactly as do_mpc/optimizer.py:843-888 (Lagrange basis through [0]+points)."""
+    from numpy.polynomial import polynomial as nppoly
+    tau = np.array([0.0] + collocation_points(deg, scheme))
+    C = np.zeros((deg + 1, deg + 1)); D = np.zeros(deg + 1)
+    for j in range(deg + 1):
+        p = np.array([1.0])
+        for r in range(deg + 1):
+            if r != j:
+                p = nppoly.polymul(p, np.array([-tau[r], 1.0]) / (tau[j] - tau[r]))
+        D[j] = nppoly.polyval(1.0, p)
+        dp = nppoly.polyder(p)
+        for r in range(deg + 1):
+            C[j, r] = nppoly.polyval(tau[r], dp)
+    return tau, C, D
+
+
+@dataclass
+class Recipe:
+    # sizes
+    n_x: int; n_u: int; n_z: int; n_tvp: int; n_pm: int; n_comb: int
+    n_eps: int; n_nl: int; N: int; n_robust: int; P: int; Pz: int; discrete: bool
+    n_y: int = 0
+    nl_rows_per_edge: int = 0
+    # tree
+    n_branches: List[int] = field(default_factory=list)
+    n_scenarios: List[int] = field(default_factory=list)
+    node_k: np.ndarray = None; node_s: np.ndarray = None
+    node_first_edge: np.ndarray = None; node_n_edges: np.ndarray = None; node_parent_edge: np.ndarray = None
+    edge_k: np.ndarray = None; edge_parent: np.ndarray = None; edge_child: np.ndarray = None
+    edge_pidx: np.ndarray = None; edge_omega: np.ndarray = None
+    # flat layout (reference order)
+    n_w: int = 0; n_g: int = 0; n_p: int = 0
+    node_x_flat: np.ndarray = None; node_u_flat: np.ndarray = None; node_eps_flat: np.ndarray = None
+    edge_yx_flat: np.ndarray = None; edge_yz_flat: np.ndarray = None; edge_g_flat: np.ndarray = None
+    p_x0: int = 0; p_tvp: int = 0; p_p: int = 0; p_uprev: int = 0
+    # symbolic atoms in scaled stage symbols
+    q: SX = None; tvp: SX = None; pp: SX = None; uprev: SX = None; xN: SX = None
+    G: SX = None            # (n_y) edge equality residuals gk (same row order as the reference's ifcn)
+    lterm: SX = None; epscost: SX = None; nl: SX = None; nl_ub: np.ndarray = None
+    rterm: SX = None; mterm: SX = None; aux: SX = None
+    xf_sel: np.ndarray = None   # indices inside y of the end-of-interval state (E y = x_child)
+    x_scaling: np.ndarray = None; u_scaling: np.ndarray = None; z_scaling: np.ndarray = None
+    opt_x_scaling: np.ndarray = None
+
+
+def build_recipe(mpc) -> Recipe:
+    """Translate a configured MPC object into the stage recipe (reference _prepare_nlp, restated stage-wise)."""
+    m, st = mpc.model, mpc.settings
+    n_x, n_u, n_z, n_tvp, n_pm = m.n_x, m.n_u, m.n_z, m.n_tvp, m.n_p
+    N, n_robust, n_comb = st.n_horizon, st.n_robust, mpc.n_combinations
+    if st.open_loop:
+        raise NotImplementedError("open_loop=True couples the inputs of all scenarios; not supported by the batched solver")
+    if st.nl_cons_single_slack and mpc.n_eps > 0:
+        raise NotImplementedError("nl_cons_single_slack couples all stages; not supported by the batched solver")
+    if m.n_w > 0:
+        pass  # process noise symbols are fixed to zero in the controller (reference _mpc.py:1166)
+    discrete = (m.model_type == "discrete")
+    deg, ni = st.collocation_deg, st.collocation_ni
+    P = 0 if discrete else (deg + 1) * ni
+    Pz = max(P, 1)
+    n_eps, n_nl = mpc.n_eps, mpc.n_nl
+    sx, su, sz = (np.asarray(v.full()).ravel() for v in (mpc._x_scaling.cat, mpc._u_scaling.cat, mpc._z_scaling.cat))
+    if n_z and n_robust > 0:
+        raise NotImplementedError("algebraic states together with n_robust>0 (reference indexing quirk, SURVEY App. F.5)")
+
+    # ---- scaled stage symbols ----------------------------------------------------------------------------
+    Xn = SX.sym("Xn", n_x); Un = SX.sym("Un", n_u); EPS = SX.sym("EPS", n_eps) if n_eps else SX.zeros(0, 1)
+    TV = SX.sym("TV", n_tvp) if n_tvp else SX.zeros(0, 1)
+    PP = SX.sym("PP", n_pm) if n_pm else SX.zeros(0, 1)
+    UPREV = SX.sym("UPREV", n_u)
+    W0 = SX.zeros(m.n_w, 1)
+    sxS, suS, szS = SX(sx.reshape(-1, 1)), SX(su.reshape(-1, 1)), SX(sz.reshape(-1, 1)) if n_z else SX.zeros(0, 1)
+
+    def rhs_scaled(x, u, z):          # optimizer.py:807-818
+        return m._rhs_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PP, W0) / sxS
+
+    def alg(x, u, z):
+        return m._alg_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PP, W0)
+
+    # ---- edge unknowns and residuals gk (optimizer.py:891-993 / :820-824) ---------------------------------
+    if discrete:
+        n_y = n_z + n_x
+        Y = SX.sym("Y", n_y)
+        zk = Y[0:n_z] if n_z else SX.zeros(0, 1)
+        xf = Y[n_z:n_y]
+        rows = []
+        if n_z:
+            rows.append(alg(Xn, Un, zk))
+        rows.append(rhs_scaled(Xn, Un, zk) - xf)        # aux variable xf (not part of the reference opt_x)
+        G = vertcat(*rows)
+        xf_sel = np.arange(n_z, n_y)
+        z_first = zk; z_last = zk
+        yx_count, yz_count = 0, n_z
+    else:
+        n_y = P * (n_x + n_z)
+        Y = SX.sym("Y", n_y)
+        _, C, D = collocation_constants(deg, st.collocation_type)
+        C[np.abs(C) < 1e-14] = 0.0; D[np.abs(D) < 1e-14] = 0.0
+        h = st.t_step / ni
+        yx = [Y[i * n_x:(i + 1) * n_x] for i in range(P)]
+        yz = [Y[P * n_x + i * n_z:P * n_x + (i + 1) * n_z] if n_z else SX.zeros(0, 1) for i in range(P)]
+        xs = [[None] * (deg + 1) for _ in range(ni)]; zs = [[None] * (deg + 1) for _ in range(ni)]
+        xs[0][0] = Xn
+        off, offz = 0, 0
+        zs[0][0] = yz[offz]; offz += 1
+        first_j = 1
+        for i in range(ni):
+            for j in range(first_j, deg + 1):
+                xs[i][j] = yx[off]; off += 1
+                zs[i][j] = yz[offz]; offz += 1
+            first_j = 0
+        xkf = yx[off]; off += 1
+        assert off == P and offz == P
+        rows = []
+        for i in range(ni):
+            if n_z:
+                rows.append(alg(xs[i][0], Un, zs[i][0]))
+            for j in range(1, deg + 1):
+                xp = SX.zeros(n_x, 1)
+                for r in range(deg + 1):
+                    if C[r, j] != 0.0:
+                        xp = xp + float(C[r, j]) * xs[i][r]
+                rows.append(h * rhs_scaled(xs[i][j], Un, zs[i][j]) - xp)
+                if n_z:
+                    rows.append(alg(xs[i][j], Un, zs[i][j]))
+            xf_i = SX.zeros(n_x, 1)
+            for r in range(deg + 1):
+                if D[r] != 0.0:
+                    xf_i = xf_i + float(D[r]) * xs[i][r]
+            x_next = xs[i + 1][0] if i + 1 < ni else xkf
+            rows.append(x_next - xf_i)
+        G = vertcat(*rows)
+        xf_sel = np.arange((P - 1) * n_x, P * n_x)
+        z_first = yz[0]; z_last = yz[P - 1]
+    assert G.shape[0] == n_y
+
+    q = vertcat(Xn, Un, EPS, Y)
+    # ---- cost / constraints per edge (_mpc.py:1228-1275), evaluated on unscaled values ----------------------
+    xu, uu = Xn * sxS, Un * suS
+    lterm = mpc.lterm_fun(xu, uu, z_last * szS if n_z else z_last, TV, PP)
+    epscost = mpc.epsterm_fun(EPS) if n_eps else SX(0.0)
+    nl_rows = []
+    if n_nl:
+        if st.nl_cons_check_colloc_points:
+            for i in range(P):
+                nl_rows.append(mpc._nl_cons_fun(yx[i] * sxS, uu, yz[i] * szS if n_z else yz[i], TV, PP, EPS))
+        else:
+            nl_rows.append(mpc._nl_cons_fun(xu, uu, z_first * szS if n_z else z_first, TV, PP, EPS))
+    nl = vertcat(*nl_rows) if nl_rows else SX.zeros(0, 1)
+    nl_ub = np.tile(np.asarray(mpc._nl_cons_ub.cat.full()).ravel(), len(nl_rows)) if nl_rows else np.zeros(0)
+    XN = SX.sym("XN", n_x)
+    mterm = mpc.mterm_fun(XN * sxS, TV, PP)
+    if mpc.flags["rterm_fun"]:
+        rterm = mpc.rterm_fun(xu, uu, UPREV, SX.zeros(n_z, 1), TV, PP)   # u_prev enters scaled (reference :1265-1269)
+        if E.depends_on(rterm.ids()[0], Xn.ids()) :
+            raise NotImplementedError("user rterm depending on the states")
+    else:
+        rf = np.asarray(mpc.rterm_factor.cat.full()).ravel()
+        rterm = SX(0.0)
+        for i in range(n_u):
+            if rf[i] != 0.0:
+                rterm = rterm + float(rf[i]) * (Un[i] - UPREV[i]) ** 2
+    aux = m._aux_expression_fun(xu, uu, z_last * szS if n_z else z_last, TV, PP)
+
+    # ---- tree tables (optimizer.py:1011-1039) ----------------------------------------------------------------
+    n_branches = [n_comb if k < n_robust else 1 for k in range(N)]
+    n_scen = [n_comb ** min(k, n_robust) for k in range(N + 1)]
+    S = n_comb ** n_robust
+    node_off = np.concatenate([[0], np.cumsum(n_scen)]).astype(int)
+    n_node = int(node_off[-1])
+    node_k = np.zeros(n_node, int); node_s = np.zeros(n_node, int)
+    node_first_edge = -np.ones(n_node, int); node_n_edges = np.zeros(n_node, int); node_parent_edge = -np.ones(n_node, int)
+    ek, ep, ec, epi, eom, egf = [], [], [], [], [], []
+    for k in range(N + 1):
+        for s in range(n_scen[k]):
+            node_k[node_off[k] + s] = k; node_s[node_off[k] + s] = s
+    nl_rows_per_edge = nl.shape[0]
+    g_row = n_x
+    for k in range(N):
+        cnt = 0
+        for s in range(n_scen[k]):
+            n = node_off[k] + s
+            node_first_edge[n] = len(ek); node_n_edges[n] = n_branches[k]
+            for b in range(n_branches[k]):
+                boff = 0 if (n_robust == 0 or k < n_robust) else s % n_branches[0]
+                e = len(ek)
+                ek.append(k); ep.append(n); ec.append(node_off[k + 1] + cnt); epi.append(b + boff)
+                eom.append(1.0 / n_scen[k + 1]); egf.append(g_row)
+                node_parent_edge[node_off[k + 1] + cnt] = e
+                g_row += (P * (n_x + n_z) if not discrete else n_z) + n_x + nl_rows_per_edge
+                cnt += 1
+    n_edge = len(ek)
+
+    # ---- flat layout -------------------------------------------------------------------------------
+    o_x = 0
+    sz_x = (N + 1) * S * (P + 1) * n_x
+    o_z = o_x + sz_x; sz_zz = N * S * Pz * n_z
+    o_u = o_z + sz_zz; sz_u = N * S * n_u
+    o_e = o_u + sz_u; sz_e = N * S * n_eps
+    n_w = o_e + sz_e
+    node_x_flat = np.array([o_x + ((node_k[n] * S + node_s[n]) * (P + 1) + P) * n_x for n in range(n_node)])
+    node_u_flat = np.array([o_u + (node_k[n] * S + node_s[n]) * n_u if node_k[n] < N else -1 for n in range(n_node)])
+    node_eps_flat = np.array([o_e + (node_k[n] * S + node_s[n]) * n_eps if node_k[n] < N else -1 for n in range(n_node)])
+    edge_yx_flat = np.array([o_x + (((ek[e] + 1) * S + node_s[ec[e]]) * (P + 1)) * n_x for e in range(n_edge)])
+    edge_yz_flat = np.array([o_z + ((ek[e] * S + node_s[ec[e]]) * Pz) * n_z for e in range(n_edge)])
+    n_p = n_x + (N + 1) * n_tvp + n_comb * n_pm + n_u
+    osc = np.ones(n_w)
+    osc[o_x:o_x + sz_x] = np.tile(sx, (N + 1) * S * (P + 1))
+    if n_z: osc[o_z:o_z + sz_zz] = np.tile(sz, N * S * Pz)
+    osc[o_u:o_u + sz_u] = np.tile(su, N * S)
+
+    return Recipe(
+        n_x=n_x, n_u=n_u, n_z=n_z, n_tvp=n_tvp, n_pm=n_pm, n_comb=n_comb, n_eps=n_eps, n_nl=n_nl, N=N,
+        n_robust=n_robust, P=P, Pz=Pz, discrete=discrete, n_y=n_y, nl_rows_per_edge=nl_rows_per_edge,
+        n_branches=n_branches, n_scenarios=n_scen,
+        node_k=node_k, node_s=node_s, node_first_edge=node_first_edge, node_n_edges=node_n_edges,
+        node_parent_edge=node_parent_edge,
+        edge_k=np.array(ek), edge_parent=np.array(ep), edge_child=np.array(ec), edge_pidx=np.array(epi),
+        edge_omega=np.array(eom), n_w=n_w, n_g=g_row, n_p=n_p,
+        node_x_flat=node_x_flat, node_u_flat=node_u_flat, node_eps_flat=node_eps_flat,
+        edge_yx_flat=edge_yx_flat, edge_yz_flat=edge_yz_flat, edge_g_flat=np.array(egf),
+        p_x0=0, p_tvp=n_x, p_p=n_x + (N + 1) * n_tvp, p_uprev=n_x + (N + 1) * n_tvp + n_comb * n_pm,
+        q=q, tvp=TV, pp=PP, uprev=UPREV, xN=XN, G=G, lterm=lterm, epscost=epscost, nl=nl, nl_ub=nl_ub,
+        rterm=rterm, mterm=mterm, aux=aux, xf_sel=xf_sel,
+        x_scaling=sx, u_scaling=su, z_scaling=sz, opt_x_scaling=osc,
+    )

@@ -1,0 +1,209 @@
+"""Code generation: stage recipe -> `problem_gen.h` (dimensions, index tables, straight-line model functions).
+
+This is the B200 counterpart of what CasADi does inside nlpsol for the reference
+(do_mpc/controller/_mpc.py:1326-1328: AD of the flat NLP + an SX virtual machine): here the edge
+Lagrangian  L_e(q) = sig_l*lterm + sig_e*epscost + lam'G + lam_nl'nl  is differentiated symbolically
+once per problem (NQ variables, not n_w), and residuals / Jacobian nonzeros / Hessian nonzeros are
+emitted as CUDA device functions that the generic interior-point kernel (csrc/ipm_core.cuh) calls for
+every (instance, edge).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import List
+
+import numpy as np
+
+from ..recipe import Recipe
+from ..sym import expr as E
+from ..sym.sx import SX
+
+_QUAL = "DMB_DEV"
+
+
+def _ctab(ctype, name, vals, fmt="{}"):
+    vals = list(vals)
+    body = ", ".join(fmt.format(v) for v in vals) if vals else ("0" if ctype == "int" else "0.0")
+    return f"DMB_TABLE const {ctype} {name}[{max(len(vals), 1)}] = {{{body}}};"
+
+
+def _dbl(v):
+    return E._fmt_const(float(v))
+
+
+def _fn(name, args, body, ret="void"):
+    return f"{_QUAL} {ret} {name}({args}) {{\n{body}\n}}\n"
+
+
+def generate(r: Recipe) -> str:
+    q_ids = r.q.ids()
+    tv_ids, pp_ids, up_ids, xn_ids = r.tvp.ids(), r.pp.ids(), r.uprev.ids(), r.xN.ids()
+    n_q = len(q_ids)
+    n_vp = r.n_x + r.n_u + r.n_eps
+    u_ids = q_ids[r.n_x:r.n_x + r.n_u]
+    inp = {}
+    for i, s in enumerate(q_ids): inp[s] = f"q[{i}]"
+    for i, s in enumerate(tv_ids): inp[s] = f"tvp[{i}]"
+    for i, s in enumerate(pp_ids): inp[s] = f"pp[{i}]"
+    sig_args = "const double* __restrict__ q, const double* __restrict__ tvp, const double* __restrict__ pp"
+
+    out: List[str] = []
+    G_ids = r.G.ids()
+    nl_ids = r.nl.ids() if r.nl.numel() else []
+    n_nl = len(nl_ids)
+    lt, ec = r.lterm.ids()[0], r.epscost.ids()[0]
+
+    # ---- residuals, cost ------------------------------------------------------------------------------------
+    out.append(_fn("gen_G", sig_args + ", double* __restrict__ g",
+                   E.emit_c([(f"g[{i}]", e) for i, e in enumerate(G_ids)], inp)))
+    out.append(_fn("gen_cost", sig_args + ", double* lt, double* ec",
+                   E.emit_c([("*lt", lt), ("*ec", ec)], inp)))
+    out.append(_fn("gen_nl", sig_args + ", double* __restrict__ d",
+                   E.emit_c([(f"d[{i}]", e) for i, e in enumerate(nl_ids)], inp) if n_nl else "  (void)d;"))
+
+    # ---- Jacobians (structural nonzeros, row-major order) ---------------------------------------------------------
+    def jac_nz(rows):
+        nz, r_, c_ = [], [], []
+        for i, ex in enumerate(rows):
+            g = E.gradient(ex, q_ids)
+            for j, d in enumerate(g):
+                if d != E.ZERO:
+                    nz.append(d); r_.append(i); c_.append(j)
+        return nz, r_, c_
+    jn, jr, jc = jac_nz(G_ids)
+    out.append(_fn("gen_J", sig_args + ", double* __restrict__ jnz",
+                   E.emit_c([(f"jnz[{k}]", e) for k, e in enumerate(jn)], inp)))
+    dn, dr, dcol = jac_nz(nl_ids)
+    out.append(_fn("gen_nl_jac", sig_args + ", double* __restrict__ dnz",
+                   E.emit_c([(f"dnz[{k}]", e) for k, e in enumerate(dn)], inp) if dn else "  (void)dnz;"))
+
+    # ---- edge Lagrangian gradient / Hessian ----------------------------------------------------------------------------
+    lam = [E.mk_sym(f"lam{i}") for i in range(len(G_ids))]
+    lnl = [E.mk_sym(f"lnl{i}") for i in range(n_nl)]
+    sig_l, sig_e = E.mk_sym("sig_l"), E.mk_sym("sig_e")
+    L = E.mk(E.ADD, E.mk(E.MUL, sig_l, lt), E.mk(E.MUL, sig_e, ec))
+    for l_, g_ in zip(lam, G_ids): L = E.mk(E.ADD, L, E.mk(E.MUL, l_, g_))
+    for l_, g_ in zip(lnl, nl_ids): L = E.mk(E.ADD, L, E.mk(E.MUL, l_, g_))
+    inpL = dict(inp)
+    for i, s in enumerate(lam): inpL[s] = f"lam[{i}]"
+    for i, s in enumerate(lnl): inpL[s] = f"lnl[{i}]"
+    inpL[sig_l] = "sig_l"; inpL[sig_e] = "sig_e"
+    gL = E.gradient(L, q_ids)
+    lag_args = sig_args + ", const double* __restrict__ lam, const double sig_l, const double sig_e, const double* __restrict__ lnl"
+    out.append(_fn("gen_lag_grad", lag_args + ", double* __restrict__ gq",
+                   "  (void)lam; (void)lnl;\n" + E.emit_c([(f"gq[{i}]", e) for i, e in enumerate(gL)], inpL)))
+    hn, hr, hc = [], [], []
+    for i in range(n_q):
+        row = E.gradient(gL[i], q_ids[:i + 1]) if gL[i] != E.ZERO else [E.ZERO] * (i + 1)
+        for j, d in enumerate(row):
+            if d != E.ZERO:
+                hn.append(d); hr.append(i); hc.append(j)
+    out.append(_fn("gen_lag_hess", lag_args + ", double* __restrict__ hnz",
+                   "  (void)lam; (void)lnl; (void)sig_l; (void)sig_e;\n" +
+                   (E.emit_c([(f"hnz[{k}]", e) for k, e in enumerate(hn)], inpL) if hn else "  (void)hnz;")))
+
+    # ---- rterm (u, u_prev, tvp) ------------------------------------------------------------------------------------------
+    inpR = {}
+    for i, s in enumerate(u_ids): inpR[s] = f"u[{i}]"
+    for i, s in enumerate(up_ids): inpR[s] = f"up[{i}]"
+    for i, s in enumerate(tv_ids): inpR[s] = f"tvp[{i}]"
+    rt = r.rterm.ids()[0]
+    if E.depends_on(rt, pp_ids) or E.depends_on(rt, [s for s in q_ids if s not in u_ids]):
+        raise NotImplementedError("rterm may only depend on (u, u_prev, tvp)")
+    ruu = list(u_ids) + list(up_ids)
+    gR = E.gradient(rt, ruu)
+    HR = [E.gradient(g, ruu) for g in gR]
+    r_args = "const double* __restrict__ u, const double* __restrict__ up, const double* __restrict__ tvp"
+    out.append(_fn("gen_rterm", r_args, "  (void)u; (void)up; (void)tvp;\n  double r;\n" + E.emit_c([("r", rt)], inpR) + "\n  return r;", "double"))
+    out.append(_fn("gen_rterm_grad", r_args + ", double* __restrict__ gr",
+                   "  (void)u; (void)up; (void)tvp;\n" + E.emit_c([(f"gr[{i}]", e) for i, e in enumerate(gR)], inpR)))
+    out.append(_fn("gen_rterm_hess", r_args + ", double* __restrict__ hr",
+                   "  (void)u; (void)up; (void)tvp;\n" +
+                   E.emit_c([(f"hr[{i * len(ruu) + j}]", HR[i][j]) for i in range(len(ruu)) for j in range(len(ruu))], inpR)))
+
+    # ---- mterm (x_N, tvp_N, p) ------------------------------------------------------------------------------------------------
+    inpM = {}
+    for i, s in enumerate(xn_ids): inpM[s] = f"x[{i}]"
+    for i, s in enumerate(tv_ids): inpM[s] = f"tvp[{i}]"
+    for i, s in enumerate(pp_ids): inpM[s] = f"pp[{i}]"
+    mt = r.mterm.ids()[0]
+    gM = E.gradient(mt, xn_ids)
+    HM = [E.gradient(g, xn_ids) for g in gM]
+    m_args = "const double* __restrict__ x, const double* __restrict__ tvp, const double* __restrict__ pp"
+    out.append(_fn("gen_mterm", m_args, "  (void)x; (void)tvp; (void)pp;\n  double r;\n" + E.emit_c([("r", mt)], inpM) + "\n  return r;", "double"))
+    out.append(_fn("gen_mterm_grad", m_args + ", double* __restrict__ gm",
+                   "  (void)x; (void)tvp; (void)pp;\n" + E.emit_c([(f"gm[{i}]", e) for i, e in enumerate(gM)], inpM)))
+    out.append(_fn("gen_mterm_hess", m_args + ", double* __restrict__ hm",
+                   "  (void)x; (void)tvp; (void)pp;\n" +
+                   E.emit_c([(f"hm[{i * r.n_x + j}]", HM[i][j]) for i in range(r.n_x) for j in range(r.n_x)], inpM)))
+    # ---- aux -------------------------------------------------------------------------------------------------------------------------
+    aux_ids = r.aux.ids()
+    out.append(_fn("gen_aux", sig_args + ", double* __restrict__ a",
+                   E.emit_c([(f"a[{i}]", e) for i, e in enumerate(aux_ids)], inp)))
+
+    # ---- header with dimensions and tables ------------------------------------------------------------------------------------------------
+    n_node = len(r.node_k)
+    node_rw = [1.0 / r.n_scenarios[k] if k < r.N else 0.0 for k in r.node_k]
+    has_dummies = int((r.P > 0) or (r.n_comb ** r.n_robust > 1))
+    H: List[str] = []
+    H.append("// GENERATED by do_mpc_b200.solver.codegen — do not edit.")
+    H.append("#pragma once")
+    H.append("#ifndef DMB_TABLE\n#ifdef DMB_HOSTSIM\n#define DMB_TABLE static\n#else\n#define DMB_TABLE static __device__\n#endif\n#endif")
+    dims = dict(NX=r.n_x, NU=r.n_u, NZ=r.n_z, NTVP=r.n_tvp, NPM=r.n_pm, NCOMB=r.n_comb, NEPS=r.n_eps, NNL=n_nl,
+                NY=r.n_y, NNODE=n_node, NEDGE=len(r.edge_k), NHOR=r.N, NW=r.n_w, NG=r.n_g, NP=r.n_p,
+                NAUX=len(aux_ids), DISCRETE=int(r.discrete), P_X0=r.p_x0, P_TVP=r.p_tvp, P_P=r.p_p, P_UPREV=r.p_uprev,
+                NNZ_J=len(jn), NNZ_H=len(hn), NNZ_D=len(dn), HAS_DUMMIES=has_dummies, NPZ=r.Pz, NPC=r.P)
+    for k, v in dims.items():
+        H.append(f"#define DMB_{k} {v}")
+    H.append(f"#define NLAM_ACTIVE {r.n_g}")
+    H.append(_ctab("int", "DMB_EDGE_K", r.edge_k)); H.append(_ctab("int", "DMB_EDGE_PARENT", r.edge_parent))
+    H.append(_ctab("int", "DMB_EDGE_CHILD", r.edge_child)); H.append(_ctab("int", "DMB_EDGE_PIDX", r.edge_pidx))
+    H.append(_ctab("double", "DMB_EDGE_OMEGA", [_dbl(v) for v in r.edge_omega]))
+    H.append(_ctab("int", "DMB_NODE_K", r.node_k)); H.append(_ctab("int", "DMB_NODE_FIRST_EDGE", r.node_first_edge))
+    H.append(_ctab("int", "DMB_NODE_NEDGE", r.node_n_edges)); H.append(_ctab("int", "DMB_NODE_PARENT_EDGE", r.node_parent_edge))
+    H.append(_ctab("double", "DMB_NODE_RW", [_dbl(v) for v in node_rw]))
+    H.append(_ctab("int", "DMB_NODE_X_FLAT", r.node_x_flat)); H.append(_ctab("int", "DMB_NODE_U_FLAT", r.node_u_flat))
+    H.append(_ctab("int", "DMB_NODE_EPS_FLAT", r.node_eps_flat))
+    H.append(_ctab("int", "DMB_EDGE_YX_FLAT", r.edge_yx_flat)); H.append(_ctab("int", "DMB_EDGE_YZ_FLAT", r.edge_yz_flat))
+    H.append(_ctab("int", "DMB_EDGE_G_FLAT", r.edge_g_flat))
+    H.append(_ctab("int", "DMB_XF_SEL", r.xf_sel))
+    H.append(_ctab("double", "DMB_INV_XSCALE", [_dbl(1.0 / v) for v in r.x_scaling]))
+    H.append(_ctab("double", "DMB_INV_USCALE", [_dbl(1.0 / v) for v in r.u_scaling]))
+    H.append(_ctab("double", "DMB_NL_UB", [_dbl(v) for v in r.nl_ub]))
+    H.append(_ctab("int", "DMB_J_ROW", jr)); H.append(_ctab("int", "DMB_J_COL", jc))
+    H.append(_ctab("int", "DMB_H_ROW", hr)); H.append(_ctab("int", "DMB_H_COL", hc))
+    H.append(_ctab("int", "DMB_D_ROW", dr)); H.append(_ctab("int", "DMB_D_COL", dcol))
+    # internal <-> flat (reference order) maps
+    n_edge = len(r.edge_k)
+    w2f = []
+    for n in range(n_node):
+        w2f += [int(r.node_x_flat[n]) + i for i in range(r.n_x)]
+        w2f += [int(r.node_u_flat[n]) + i if r.node_u_flat[n] >= 0 else -1 for i in range(r.n_u)]
+        w2f += [int(r.node_eps_flat[n]) + i if r.node_eps_flat[n] >= 0 else -1 for i in range(r.n_eps)]
+    for e in range(n_edge):
+        if r.discrete:
+            w2f += [int(r.edge_yz_flat[e]) + i for i in range(r.n_z)] + [-1] * r.n_x
+        else:
+            w2f += [int(r.edge_yx_flat[e]) + i for i in range(r.P * r.n_x)]
+            w2f += [int(r.edge_yz_flat[e]) + i for i in range(r.P * r.n_z)]
+    l2f = list(range(r.n_x))
+    for e in range(n_edge):
+        g0 = int(r.edge_g_flat[e])
+        if r.discrete:
+            l2f += [g0 + i for i in range(r.n_z)] + [-1] * r.n_x
+            l2f += [g0 + r.n_z + i for i in range(r.n_x)]
+            l2f += [g0 + r.n_z + r.n_x + i for i in range(n_nl)]
+        else:
+            l2f += [g0 + i for i in range(r.n_y + r.n_x + n_nl)]
+    assert len(w2f) == n_node * n_vp + n_edge * r.n_y
+    H.append("#define DMB_W2FLAT_INIT {" + ", ".join(str(v) for v in w2f) + "}")
+    H.append("#define DMB_LAM2FLAT_INIT {" + ", ".join(str(v) for v in l2f) + "}")
+    H.append(f"DMB_TABLE const int DMB_W2FLAT[{len(w2f)}] = DMB_W2FLAT_INIT;")
+    H.append(f"DMB_TABLE const int DMB_LAM2FLAT[{len(l2f)}] = DMB_LAM2FLAT_INIT;")
+    H.append("")
+    src = "\n".join(H) + "\n" + "\n".join(out)
+    return src
+
+
+def source_hash(src: str, extra: str = "") -> str:
+    return hashlib.sha256((src + extra).encode()).hexdigest()[:16]
