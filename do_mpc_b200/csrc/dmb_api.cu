@@ -1,0 +1,302 @@
+// C-ABI + persistent solve kernel of the batched NLP solver (see include/dompc_b200.h).
+// Compiled once per generated problem (problem_gen.h on the include path) for sm_100a.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <new>
+
+#include "ipm_solve.cuh"
+#include "dmb_host_util.h"
+#include "dompc_b200.h"
+
+#ifndef DMB_THREADS
+#define DMB_THREADS 128
+#endif
+#ifndef DMB_VEC_SMEM
+#define DMB_VEC_SMEM 1
+#endif
+#define DMB_NWARP (DMB_THREADS / 32)
+
+// ---- shared memory carve-up (doubles first, then the small struct) ----------------------------------------
+#define SM_TILE 0
+#define SM_HQ (SM_TILE + DMB_NWARP * NY * TILE_LD)
+#define SM_QS (SM_HQ + DMB_NWARP * NQ * HQ_LD)
+#define SM_VEC (SM_QS + DMB_QS_SIZE)
+#define SM_DOUBLES (SM_VEC + (DMB_VEC_SMEM ? WV_END : 0))
+#define SM_BYTES (SM_DOUBLES * sizeof(double) + sizeof(DmbShared) + 16)
+// per-CTA global workspace slot
+#define SLOT_DOUBLES ((DMB_VEC_SMEM ? 0 : WV_END) + NEDGE * WS_EDGE + NNODE * WN_NODE)
+
+struct KernelArgs {
+  int B;
+  const double *x_init, *x0s, *u0s, *z0s, *p, *lbI, *ubI;
+  double *x, *lam_g, *lam_x, *g, *f, *u0, *stats, *ws;
+  int *status, *iters, *counter;
+  DmbOptions o;
+};
+
+__global__ void __launch_bounds__(DMB_THREADS) dmb_solve_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  DmbShared* S = reinterpret_cast<DmbShared*>(sm + SM_DOUBLES);
+  __shared__ int cur;
+  __shared__ DmbResult result;
+  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5)};
+  double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
+  Inst I;
+  bind_instance(I, DMB_VEC_SMEM ? sm + SM_VEC : slot, slot + (DMB_VEC_SMEM ? 0 : WV_END));
+  I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0;
+  I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
+  while (true) {
+    if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int b = cur;
+    __syncthreads();
+    if (b >= a.B) break;
+    I.p = a.p + (size_t)b * DMB_NP;
+    load_initial_guess(c, a.x_init ? a.x_init + (size_t)b * DMB_NW : nullptr, a.x0s ? a.x0s + (size_t)b * NX : nullptr,
+                       a.u0s ? a.u0s + (size_t)b * NU : nullptr, a.z0s ? a.z0s + (size_t)b * DMB_NZ : nullptr, I.wt);
+    solve_instance(c, I, a.o, I.wt, sm + SM_TILE, sm + SM_HQ, sm + SM_QS, S, &result);
+    const double df = result.df;
+    if (a.x && a.x_init)
+      for (int i = c.tid; i < DMB_NW; i += c.nthr) a.x[(size_t)b * DMB_NW + i] = a.x_init[(size_t)b * DMB_NW + i];
+    __syncthreads();
+    store_solution(c, I, df, a.x ? a.x + (size_t)b * DMB_NW : nullptr, a.lam_g ? a.lam_g + (size_t)b * DMB_NG : nullptr,
+                   a.lam_x ? a.lam_x + (size_t)b * DMB_NW : nullptr, a.g ? a.g + (size_t)b * DMB_NG : nullptr);
+    for (int i = c.tid; i < NU; i += c.nthr) a.u0[(size_t)b * NU + i] = I.w[NODE_OFF(0) + NX + i];
+    if (threadIdx.x == 0) {
+      a.f[b] = result.f; a.status[b] = result.status; a.iters[b] = result.iters;
+      if (a.stats) {
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_MU] = result.mu;
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_INF_PR] = result.inf_pr;
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_INF_DU] = result.inf_du;
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_OBJ_SCALE] = result.df;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// broadcast-free fill of x for the cold-start path when the caller wants the full primal vector:
+// unused reference variables keep the broadcast initial guess (reference _mpc.py:969-971)
+__global__ void dmb_fill_guess_kernel(int B, const double* x0s, const double* u0s, const double* z0s, double* x) {
+  const int S = DMB_NW;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)B * S; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / S), i = (int)(idx % S);
+    const int nxall = (DMB_NHOR + 1) * DMB_NSCEN * (DMB_NPC + 1) * NX;
+    const int nzall = DMB_NHOR * DMB_NSCEN * DMB_NPZ * DMB_NZ;
+    const int nuall = DMB_NHOR * DMB_NSCEN * NU;
+    double v = 0.0;
+    if (i < nxall) v = x0s[(size_t)b * NX + i % NX];
+    else if (i < nxall + nzall) v = z0s ? z0s[(size_t)b * DMB_NZ + (i - nxall) % (DMB_NZ > 0 ? DMB_NZ : 1)] : 0.0;
+    else if (i < nxall + nzall + nuall) v = u0s[(size_t)b * NU + (i - nxall - nzall) % NU];
+    x[idx] = v;
+  }
+}
+
+// aux expressions for every (k, s): thread per (instance, k, s)
+__global__ void dmb_aux_kernel(int B, const double* x, const double* p, double* aux) {
+  const int per = DMB_NHOR * DMB_NSCEN;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)B * per; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per), ks = (int)(idx % per);
+    // node (k, s); scenario slots beyond the populated ones repeat the last one (reference _mpc.py:1282-1284)
+    const int n = DMB_KS_NODE[ks];
+    const int e = DMB_NODE_FIRST_EDGE[n] + DMB_NODE_NEDGE[n] - 1;
+    const double* xb = x + (size_t)b * DMB_NW;
+    const double* pb = p + (size_t)b * DMB_NP;
+    double q[NQ], a[DMB_NAUX > 0 ? DMB_NAUX : 1];
+    for (int i = 0; i < NVP; ++i) { const int fl = DMB_W2FLAT[NODE_OFF(n) + i]; q[i] = fl >= 0 ? xb[fl] : 0.0; }
+    for (int i = 0; i < NY; ++i) { const int fl = DMB_W2FLAT[EDGE_OFF(e) + i]; q[NVP + i] = fl >= 0 ? xb[fl] : 0.0; }
+    gen_aux(q, edge_tvp(pb, e), edge_pp(pb, e), a);
+    for (int i = 0; i < DMB_NAUX; ++i) aux[((size_t)b * per + ks) * DMB_NAUX + i] = a[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct dmb_solver {
+  int device = 0, n_sm = 0, grid_max = 0, have_bounds = 0;
+  DmbOptions opts;
+  double *d_lbI = nullptr, *d_ubI = nullptr, *d_ws = nullptr;
+  int* d_counter = nullptr;
+  size_t ws_slots = 0;
+  // staging for the host entry point
+  double* d_stage = nullptr; size_t stage_doubles = 0;
+  double* h_stage = nullptr; size_t h_stage_doubles = 0;
+  int last_grid = 0; long long n_launches = 0; float last_ms = 0.f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { s->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DMB_E_CUDA; } } while (0)
+
+extern "C" {
+
+int dmb_abi_version(void) { return DMB_ABI_VERSION; }
+
+void dmb_get_dims(int* d) {
+  d[DMB_DIM_NW] = DMB_NW; d[DMB_DIM_NG] = DMB_NG; d[DMB_DIM_NP] = DMB_NP; d[DMB_DIM_NX] = NX; d[DMB_DIM_NU] = NU;
+  d[DMB_DIM_NZ] = DMB_NZ; d[DMB_DIM_NAUX] = DMB_NAUX; d[DMB_DIM_NHOR] = DMB_NHOR; d[DMB_DIM_NSCEN] = DMB_NSCEN;
+  d[DMB_DIM_NEDGE] = NEDGE; d[DMB_DIM_NNODE] = NNODE; d[DMB_DIM_OPTSIZE] = (int)sizeof(DmbOptions);
+  d[DMB_DIM_THREADS] = DMB_THREADS; d[DMB_DIM_SMEM] = (int)SM_BYTES; d[DMB_DIM_WS_DOUBLES] = (int)SLOT_DOUBLES;
+}
+
+void dmb_default_options(DmbOptions* o) { dmb_fill_default_options(o); }
+
+dmb_solver* dmb_create(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) return nullptr;
+  dmb_solver* s = new (std::nothrow) dmb_solver();
+  if (!s) return nullptr;
+  s->device = device;
+  dmb_fill_default_options(&s->opts);
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return nullptr; }
+  s->n_sm = prop.multiProcessorCount;
+  if (cudaFuncSetAttribute(dmb_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES) != cudaSuccess) { delete s; return nullptr; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmb_solve_kernel, DMB_THREADS, SM_BYTES) != cudaSuccess || per_sm < 1) { delete s; return nullptr; }
+  s->grid_max = per_sm * s->n_sm;
+  bool ok = cudaMalloc(&s->d_lbI, sizeof(double) * NWI) == cudaSuccess && cudaMalloc(&s->d_ubI, sizeof(double) * NWI) == cudaSuccess &&
+            cudaMalloc(&s->d_counter, sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&s->d_ws, sizeof(double) * (size_t)SLOT_DOUBLES * s->grid_max) == cudaSuccess &&
+            cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+  if (!ok) { dmb_destroy(s); return nullptr; }
+  s->ws_slots = s->grid_max;
+  return s;
+}
+
+void dmb_destroy(dmb_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_lbI); cudaFree(s->d_ubI); cudaFree(s->d_counter); cudaFree(s->d_ws); cudaFree(s->d_stage);
+  if (s->h_stage) cudaFreeHost(s->h_stage);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+const char* dmb_last_error(dmb_solver* s) { return s ? s->err.c_str() : "null solver handle"; }
+
+int dmb_set_options(dmb_solver* s, const DmbOptions* o, int size) {
+  if (!s || !o || size != (int)sizeof(DmbOptions)) return DMB_E_ARG;
+  s->opts = *o;
+  s->have_bounds = 0;     // relaxed bounds depend on the options
+  return DMB_E_OK;
+}
+
+int dmb_set_bounds(dmb_solver* s, const double* lbx, const double* ubx) {
+  if (!s || !lbx || !ubx) return DMB_E_ARG;
+  CK(cudaSetDevice(s->device));
+  static thread_local double lbI[NWI], ubI[NWI];
+  dmb_internal_bounds(lbx, ubx, &s->opts, lbI, ubI);
+  CK(cudaMemcpy(s->d_lbI, lbI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_ubI, ubI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
+  s->have_bounds = 1;
+  return DMB_E_OK;
+}
+
+int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double* d_x0s, const double* d_u0s,
+                     const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x, double* d_g,
+                     double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* stream_) {
+  if (!s) return DMB_E_ARG;
+  if (B <= 0 || !d_p || !d_f || !d_status || !d_iters || !d_u0 || (!d_x_init && (!d_x0s || !d_u0s)) ||
+      (!d_x_init && DMB_NZ > 0 && !d_z0s)) { s->err = "invalid argument"; return DMB_E_ARG; }
+  if (!s->have_bounds) { s->err = "dmb_set_bounds must be called before solving"; return DMB_E_STATE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), st));
+  KernelArgs a;
+  a.B = B; a.x_init = d_x_init; a.x0s = d_x0s; a.u0s = d_u0s; a.z0s = d_z0s; a.p = d_p; a.lbI = s->d_lbI; a.ubI = s->d_ubI;
+  a.x = d_x; a.lam_g = d_lam_g; a.lam_x = d_lam_x; a.g = d_g; a.f = d_f; a.u0 = d_u0; a.stats = d_stats; a.ws = s->d_ws;
+  a.status = d_status; a.iters = d_iters; a.counter = s->d_counter; a.o = s->opts;
+  const int grid = B < s->grid_max ? B : s->grid_max;
+  if (d_x && !d_x_init) {
+    dmb_fill_guess_kernel<<<s->n_sm * 4, 256, 0, st>>>(B, d_x0s, d_u0s, d_z0s, d_x);
+    a.x_init = nullptr;
+    s->n_launches++;
+  }
+  CK(cudaEventRecord(s->ev0, st));
+  dmb_solve_kernel<<<grid, DMB_THREADS, SM_BYTES, st>>>(a);
+  CK(cudaEventRecord(s->ev1, st));
+  CK(cudaGetLastError());
+  s->last_grid = grid; s->n_launches++;
+  return DMB_E_OK;
+}
+
+static int ensure_stage(dmb_solver* s, size_t doubles) {
+  if (doubles > s->stage_doubles) {
+    cudaFree(s->d_stage); s->d_stage = nullptr; s->stage_doubles = 0;
+    CK(cudaMalloc(&s->d_stage, doubles * sizeof(double)));
+    s->stage_doubles = doubles;
+  }
+  return DMB_E_OK;
+}
+
+int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s,
+                   const double* p, double* x, double* lam_g, double* lam_x, double* g, double* f, int* status,
+                   int* iters, double* u0, double* stats) {
+  if (!s) return DMB_E_ARG;
+  if (B <= 0 || !p || !f || !status || !iters || !u0) { s->err = "invalid argument"; return DMB_E_ARG; }
+  CK(cudaSetDevice(s->device));
+  const size_t nB = (size_t)B;
+  // device layout of the staging buffer (doubles)
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 1) & ~(size_t)1; return o; };
+  const size_t o_p = take(nB * DMB_NP), o_xi = take(x_init ? nB * DMB_NW : 0), o_x0 = take(x0s ? nB * NX : 0),
+               o_u0s = take(u0s ? nB * NU : 0), o_z0 = take(z0s ? nB * DMB_NZ : 0), o_x = take(x ? nB * DMB_NW : 0),
+               o_lg = take(lam_g ? nB * DMB_NG : 0), o_lx = take(lam_x ? nB * DMB_NW : 0), o_g = take(g ? nB * DMB_NG : 0),
+               o_f = take(nB), o_u = take(nB * NU), o_st = take(stats ? nB * DMB_NSTAT : 0), o_i1 = take(nB), o_i2 = take(nB);
+  int rc = ensure_stage(s, off);
+  if (rc) return rc;
+  double* d = s->d_stage;
+  CK(cudaMemcpyAsync(d + o_p, p, nB * DMB_NP * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (x_init) CK(cudaMemcpyAsync(d + o_xi, x_init, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (x0s) CK(cudaMemcpyAsync(d + o_x0, x0s, nB * NX * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (u0s) CK(cudaMemcpyAsync(d + o_u0s, u0s, nB * NU * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (z0s && DMB_NZ > 0) CK(cudaMemcpyAsync(d + o_z0, z0s, nB * DMB_NZ * sizeof(double), cudaMemcpyHostToDevice, 0));
+  rc = dmb_solve_device(s, B, x_init ? d + o_xi : nullptr, x0s ? d + o_x0 : nullptr, u0s ? d + o_u0s : nullptr,
+                        (z0s && DMB_NZ > 0) ? d + o_z0 : nullptr, d + o_p, x ? d + o_x : nullptr, lam_g ? d + o_lg : nullptr,
+                        lam_x ? d + o_lx : nullptr, g ? d + o_g : nullptr, d + o_f, (int*)(d + o_i1), (int*)(d + o_i2),
+                        d + o_u, stats ? d + o_st : nullptr, nullptr);
+  if (rc) return rc;
+  if (x) CK(cudaMemcpyAsync(x, d + o_x, nB * DMB_NW * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (lam_g) CK(cudaMemcpyAsync(lam_g, d + o_lg, nB * DMB_NG * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (lam_x) CK(cudaMemcpyAsync(lam_x, d + o_lx, nB * DMB_NW * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (g) CK(cudaMemcpyAsync(g, d + o_g, nB * DMB_NG * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (stats) CK(cudaMemcpyAsync(stats, d + o_st, nB * DMB_NSTAT * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(f, d + o_f, nB * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(u0, d + o_u, nB * NU * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(status, d + o_i1, nB * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(iters, d + o_i2, nB * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+  return DMB_E_OK;
+}
+
+int dmb_aux_host(dmb_solver* s, int B, const double* x, const double* p, double* aux) {
+  if (!s || B <= 0 || !x || !p || !aux) return DMB_E_ARG;
+  CK(cudaSetDevice(s->device));
+  const size_t nB = (size_t)B, na = nB * DMB_NHOR * DMB_NSCEN * (DMB_NAUX > 0 ? DMB_NAUX : 1);
+  int rc = ensure_stage(s, nB * DMB_NW + nB * DMB_NP + na + 8);
+  if (rc) return rc;
+  double* d = s->d_stage;
+  CK(cudaMemcpy(d, x, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d + nB * DMB_NW, p, nB * DMB_NP * sizeof(double), cudaMemcpyHostToDevice));
+  dmb_aux_kernel<<<(int)((nB * DMB_NHOR * DMB_NSCEN + 127) / 128), 128>>>(B, d, d + nB * DMB_NW, d + nB * DMB_NW + nB * DMB_NP);
+  CK(cudaGetLastError());
+  s->n_launches++;
+  CK(cudaMemcpy(aux, d + nB * DMB_NW + nB * DMB_NP, nB * DMB_NHOR * DMB_NSCEN * DMB_NAUX * sizeof(double), cudaMemcpyDeviceToHost));
+  return DMB_E_OK;
+}
+
+int dmb_get_stats(dmb_solver* s, int* grid, int* block, int* smem_bytes, long long* n_launches, float* last_kernel_ms) {
+  if (!s) return DMB_E_ARG;
+  if (grid) *grid = s->last_grid;
+  if (block) *block = DMB_THREADS;
+  if (smem_bytes) *smem_bytes = (int)SM_BYTES;
+  if (n_launches) *n_launches = s->n_launches;
+  if (last_kernel_ms) { cudaEventSynchronize(s->ev1); cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1); *last_kernel_ms = s->last_ms; }
+  return DMB_E_OK;
+}
+
+}  // extern "C"

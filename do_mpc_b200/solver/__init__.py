@@ -1,0 +1,197 @@
+"""BatchedNlpSolver — the object installed as `mpc.S` in place of CasADi's nlpsol Function.
+
+Reference boundary: `self.S = castools.nlpsol('S','ipopt',nlp,opts)` (do_mpc/controller/_mpc.py:1328),
+called as `r = self.S(x0=,lbx=,ubx=,lbg=,ubg=,p=[,lam_x0=,lam_g0=])` and `self.S.stats()` (do_mpc/optimizer.py:754-778).
+This class keeps that call signature and return keys, and adds the batch entry points.  All numerics run in
+the generated CUDA library through the C ABI of include/dompc_b200.h (ctypes); there is NO CPU fallback —
+constructing the solver without a visible B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from typing import Optional
+
+import numpy as np
+
+from ..sym.sx import DM
+from .build import build_library
+from .options import DmbOptions, apply_nlpsol_opts
+
+_STATUS_NAMES = {0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", 2: "Infeasible_Problem_Detected",
+                 -1: "Maximum_Iterations_Exceeded", -2: "Restoration_Failed", -3: "Error_In_Step_Computation",
+                 -13: "Invalid_Number_Detected", -100: "Not_Run"}
+(DIM_NW, DIM_NG, DIM_NP, DIM_NX, DIM_NU, DIM_NZ, DIM_NAUX, DIM_NHOR, DIM_NSCEN, DIM_NEDGE, DIM_NNODE, DIM_OPTSIZE,
+ DIM_THREADS, DIM_SMEM, DIM_WS, DIM_COUNT) = range(16)
+NSTAT = 4
+
+_c_dp = ctypes.c_void_p
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _as2d(a, n):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, n))
+
+
+def load_library(path):
+    lib = ctypes.CDLL(str(path))
+    lib.dmb_abi_version.restype = ctypes.c_int
+    lib.dmb_create.restype = ctypes.c_void_p
+    lib.dmb_create.argtypes = [ctypes.c_int]
+    lib.dmb_destroy.argtypes = [ctypes.c_void_p]
+    lib.dmb_last_error.restype = ctypes.c_char_p
+    lib.dmb_last_error.argtypes = [ctypes.c_void_p]
+    lib.dmb_set_options.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.dmb_set_bounds.argtypes = [ctypes.c_void_p, _c_dp, _c_dp]
+    lib.dmb_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 14
+    lib.dmb_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 15
+    lib.dmb_aux_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dp, _c_dp, _c_dp]
+    lib.dmb_get_stats.argtypes = [ctypes.c_void_p] + [_c_dp] * 5
+    return lib
+
+
+class BatchedNlpSolver:
+    def __init__(self, recipe, nlpsol_opts=None, device: Optional[int] = None):
+        self.recipe = recipe
+        self.lib_path = build_library(recipe)
+        self.lib = load_library(self.lib_path)
+        dims = (ctypes.c_int * DIM_COUNT)()
+        self.lib.dmb_get_dims(dims)
+        self.dims = list(dims)
+        self.n_w, self.n_g, self.n_p = self.dims[DIM_NW], self.dims[DIM_NG], self.dims[DIM_NP]
+        self.n_x, self.n_u, self.n_z, self.n_aux = (self.dims[i] for i in (DIM_NX, DIM_NU, DIM_NZ, DIM_NAUX))
+        assert (self.n_w, self.n_g, self.n_p) == (recipe.n_w, recipe.n_g, recipe.n_p)
+        assert self.dims[DIM_OPTSIZE] == ctypes.sizeof(DmbOptions), "DmbOptions layout mismatch between Python and CUDA"
+        self.options = DmbOptions()
+        self.lib.dmb_default_options(ctypes.byref(self.options))
+        apply_nlpsol_opts(self.options, nlpsol_opts)
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0")) if "DMB_DEVICE" not in os.environ else int(os.environ["DMB_DEVICE"])
+        self.device = device
+        self._h = self.lib.dmb_create(device)
+        if not self._h:
+            raise RuntimeError(
+                "do_mpc_b200: could not create the CUDA solver (no usable GPU / sm_100a kernel image cannot be loaded). "
+                "This package has no CPU fallback for the NLP solve.")
+        rc = self.lib.dmb_set_options(self._h, ctypes.byref(self.options), ctypes.sizeof(DmbOptions))
+        self._check(rc)
+        self._bounds_key = None
+        self._stats = {"success": False, "return_status": "Not_Run", "iter_count": 0, "t_wall_total": 0.0}
+        self.n_launches_timed = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.lib.dmb_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"do_mpc_b200 CUDA solver error {rc}: {self.lib.dmb_last_error(self._h).decode()}")
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            setattr(self.options, k, v)
+        self._check(self.lib.dmb_set_options(self._h, ctypes.byref(self.options), ctypes.sizeof(DmbOptions)))
+        self._bounds_key = None
+
+    def _set_bounds(self, lbx, ubx):
+        lbx = np.ascontiguousarray(np.asarray(lbx, dtype=np.float64).ravel())
+        ubx = np.ascontiguousarray(np.asarray(ubx, dtype=np.float64).ravel())
+        key = (lbx.tobytes(), ubx.tobytes())
+        if key != self._bounds_key:
+            assert lbx.size == self.n_w and ubx.size == self.n_w, "bounds must have n_w entries"
+            self._check(self.lib.dmb_set_bounds(self._h, _ptr(lbx), _ptr(ubx)))
+            self._bounds_key = key
+
+    # ---- batched host entry point --------------------------------------------------------------------------------
+    def solve_batch(self, P, x0s=None, u0s=None, z0s=None, lbx=None, ubx=None, x_init=None, return_full=False):
+        """P [B,n_p]; initial guess = x_init [B,n_w] (scaled) or broadcast of x0s,u0s,z0s (scaled). Host arrays."""
+        P = _as2d(P, self.n_p)
+        B = P.shape[0]
+        if lbx is not None:
+            self._set_bounds(lbx, ubx)
+        x_init = None if x_init is None else _as2d(x_init, self.n_w)
+        x0s = None if x0s is None else _as2d(x0s, self.n_x)
+        u0s = None if u0s is None else _as2d(u0s, self.n_u)
+        z0s = None if (z0s is None or self.n_z == 0) else _as2d(z0s, self.n_z)
+        f = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+        u0 = np.empty((B, self.n_u)); stats = np.empty((B, NSTAT))
+        x = lam_g = lam_x = g = None
+        if return_full:
+            x = np.empty((B, self.n_w)); lam_g = np.empty((B, self.n_g)); lam_x = np.empty((B, self.n_w)); g = np.empty((B, self.n_g))
+        t0 = time.perf_counter()
+        rc = self.lib.dmb_solve_host(self._h, B, _ptr(x_init), _ptr(x0s), _ptr(u0s), _ptr(z0s), _ptr(P), _ptr(x),
+                                     _ptr(lam_g), _ptr(lam_x), _ptr(g), _ptr(f), _ptr(status), _ptr(iters), _ptr(u0), _ptr(stats))
+        self._check(rc)
+        t = time.perf_counter() - t0
+        out = {"u0_scaled": u0, "f": f, "status": status, "iter_count": iters, "success": (status == 0) | (status == 1),
+               "stats": stats, "t_wall_total": t}
+        if return_full:
+            out.update(x=x, lam_g=lam_g, lam_x=lam_x, g=g)
+        return out
+
+    # ---- device-resident entry point (torch tensors as memory containers) ----------------------------------------------
+    def solve_batch_device(self, P, x0s=None, u0s=None, z0s=None, x_init=None, out=None, stream=None, want_full=False):
+        """All arguments are CUDA float64 torch tensors on this solver's device; returns dict of CUDA tensors.
+        Asynchronous with respect to the host (kernel queued on `stream` or the current torch stream)."""
+        import torch
+        B = P.shape[0]
+        dev = P.device
+        def dp(t): return None if t is None else ctypes.c_void_p(t.data_ptr())
+        if out is None:
+            out = {"f": torch.empty(B, dtype=torch.float64, device=dev), "status": torch.empty(B, dtype=torch.int32, device=dev),
+                   "iter_count": torch.empty(B, dtype=torch.int32, device=dev),
+                   "u0_scaled": torch.empty(B, self.n_u, dtype=torch.float64, device=dev),
+                   "stats": torch.empty(B, NSTAT, dtype=torch.float64, device=dev)}
+            if want_full:
+                out.update(x=torch.empty(B, self.n_w, dtype=torch.float64, device=dev),
+                           lam_g=torch.empty(B, self.n_g, dtype=torch.float64, device=dev),
+                           lam_x=torch.empty(B, self.n_w, dtype=torch.float64, device=dev),
+                           g=torch.empty(B, self.n_g, dtype=torch.float64, device=dev))
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.dmb_solve_device(self._h, B, dp(x_init), dp(x0s), dp(u0s), dp(z0s), dp(P), dp(out.get("x")),
+                                       dp(out.get("lam_g")), dp(out.get("lam_x")), dp(out.get("g")), dp(out["f"]),
+                                       dp(out["status"]), dp(out["iter_count"]), dp(out["u0_scaled"]), dp(out["stats"]),
+                                       ctypes.c_void_p(st.cuda_stream))
+        self._check(rc)
+        return out
+
+    # ---- nlpsol-Function look-alike ------------------------------------------------------------------------------------------------
+    def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_x0=None, lam_g0=None):
+        """Single-instance call with the keyword signature of the CasADi nlpsol Function (optimizer.py:754-770).
+        lam_x0/lam_g0 are accepted and ignored exactly like IPOPT without warm_start_init_point."""
+        def arr(v):
+            return np.asarray(v.full() if hasattr(v, "full") else v, dtype=np.float64).ravel()
+        x0, p = arr(x0), arr(p)
+        if x0.size != self.n_w or p.size != self.n_p:
+            raise ValueError(f"nlpsol call: x0 has {x0.size} (expected {self.n_w}), p has {p.size} (expected {self.n_p})")
+        r = self.solve_batch(p[None, :], x_init=x0[None, :], lbx=arr(lbx), ubx=arr(ubx), return_full=True)
+        st = int(r["status"][0])
+        self._stats = {"success": bool(r["success"][0]), "return_status": _STATUS_NAMES.get(st, str(st)),
+                       "iter_count": int(r["iter_count"][0]), "t_wall_total": r["t_wall_total"],
+                       "t_wall_S": r["t_wall_total"], "unified_return_status": "SOLVER_RET_SUCCESS" if r["success"][0] else "SOLVER_RET_UNKNOWN"}
+        return {"x": DM(r["x"][0]), "f": DM(r["f"][0]), "g": DM(r["g"][0]), "lam_g": DM(r["lam_g"][0]),
+                "lam_x": DM(r["lam_x"][0]), "lam_p": DM(np.zeros(self.n_p))}
+
+    def stats(self):
+        return dict(self._stats)
+
+    def aux(self, x, p):
+        x = _as2d(x.full() if hasattr(x, "full") else x, self.n_w); p = _as2d(p.full() if hasattr(p, "full") else p, self.n_p)
+        B = x.shape[0]
+        out = np.zeros((B, self.dims[DIM_NHOR] * self.dims[DIM_NSCEN] * self.n_aux))
+        self._check(self.lib.dmb_aux_host(self._h, B, _ptr(x), _ptr(p), _ptr(out)))
+        return out[0] if B == 1 else out
+
+    def launch_info(self):
+        grid = ctypes.c_int(); block = ctypes.c_int(); smem = ctypes.c_int(); n = ctypes.c_longlong(); ms = ctypes.c_float()
+        self.lib.dmb_get_stats(self._h, ctypes.byref(grid), ctypes.byref(block), ctypes.byref(smem), ctypes.byref(n), ctypes.byref(ms))
+        return {"grid": grid.value, "block": block.value, "smem_bytes": smem.value, "n_launches": n.value, "last_kernel_ms": ms.value}

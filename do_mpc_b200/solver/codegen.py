@@ -152,7 +152,8 @@ def generate(r: Recipe) -> str:
     dims = dict(NX=r.n_x, NU=r.n_u, NZ=r.n_z, NTVP=r.n_tvp, NPM=r.n_pm, NCOMB=r.n_comb, NEPS=r.n_eps, NNL=n_nl,
                 NY=r.n_y, NNODE=n_node, NEDGE=len(r.edge_k), NHOR=r.N, NW=r.n_w, NG=r.n_g, NP=r.n_p,
                 NAUX=len(aux_ids), DISCRETE=int(r.discrete), P_X0=r.p_x0, P_TVP=r.p_tvp, P_P=r.p_p, P_UPREV=r.p_uprev,
-                NNZ_J=len(jn), NNZ_H=len(hn), NNZ_D=len(dn), HAS_DUMMIES=has_dummies, NPZ=r.Pz, NPC=r.P)
+                NNZ_J=len(jn), NNZ_H=len(hn), NNZ_D=len(dn), HAS_DUMMIES=has_dummies, NPZ=r.Pz, NPC=r.P,
+                NSCEN=r.n_comb ** r.n_robust)
     for k, v in dims.items():
         H.append(f"#define DMB_{k} {v}")
     H.append(f"#define NLAM_ACTIVE {r.n_g}")
@@ -167,6 +168,12 @@ def generate(r: Recipe) -> str:
     H.append(_ctab("int", "DMB_EDGE_YX_FLAT", r.edge_yx_flat)); H.append(_ctab("int", "DMB_EDGE_YZ_FLAT", r.edge_yz_flat))
     H.append(_ctab("int", "DMB_EDGE_G_FLAT", r.edge_g_flat))
     H.append(_ctab("int", "DMB_XF_SEL", r.xf_sel))
+    S_ = r.n_comb ** r.n_robust
+    ks_node = []
+    for k in range(r.N):
+        nodes_k = [n for n in range(n_node) if r.node_k[n] == k]
+        ks_node += [nodes_k[min(s_, len(nodes_k) - 1)] for s_ in range(S_)]
+    H.append(_ctab("int", "DMB_KS_NODE", ks_node))
     H.append(_ctab("double", "DMB_INV_XSCALE", [_dbl(1.0 / v) for v in r.x_scaling]))
     H.append(_ctab("double", "DMB_INV_USCALE", [_dbl(1.0 / v) for v in r.u_scaling]))
     H.append(_ctab("double", "DMB_NL_UB", [_dbl(v) for v in r.nl_ub]))

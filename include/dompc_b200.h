@@ -1,0 +1,87 @@
+/* dompc_b200.h — C ABI of the B200 batched NLP solver that stands in for CasADi's nlpsol('ipopt') Function
+ * on do-mpc's controller path.
+ *
+ * Every generated problem library (one shared object per MPC configuration, built by
+ * do_mpc_b200/solver/build.py from csrc/dmb_api.cu + the generated problem_gen.h) exports exactly
+ * these symbols.  Plain pointers and sizes only; no torch / CasADi types.
+ *
+ * Reference interfaces replaced (file:line in the do-mpc tree):
+ *   dmb_create / dmb_destroy     <-> castools.nlpsol('S','ipopt',nlp,opts)      do_mpc/controller/_mpc.py:1326-1328
+ *   dmb_set_options              <-> settings.nlpsol_opts passed to nlpsol       do_mpc/controller/_mpc.py:1328
+ *   dmb_set_bounds               <-> lbx/ubx arguments of S(...)                 do_mpc/optimizer.py:756-757
+ *   dmb_solve_host               <-> r = self.S(x0=,lbx=,ubx=,lbg=,ubg=,p=)      do_mpc/optimizer.py:754-777
+ *                                    (B instances per call; x/g/lam_g/lam_x/f as in the returned dict)
+ *   dmb_solve_device             <-> same call with device-resident batches (no reference counterpart:
+ *                                    the reference is single-instance, host only)
+ *   dmb_get_stats                <-> S.stats()                                    do_mpc/optimizer.py:778
+ *   dmb_aux_host                 <-> opt_aux_expression_fun(opt_x, opt_p)         do_mpc/controller/_mpc.py:1331
+ *
+ * Layouts: all vectors are the reference's flat vectors: opt_x (n_w, scaled
+ * variables), opt_p (n_p), g / lam_g (n_g), row-major over the batch: element i of instance b at [b*n + i].
+ * Equality rows have lbg = ubg = 0 and inequality rows -inf <= g <= ub exactly as the MPC builds them, so
+ * lbg/ubg are compiled into the library and not passed.
+ *
+ * Errors: functions return 0 on success, a negative DMB_E_* code otherwise (no exceptions, no aborts).
+ * A failed NLP solve is NOT an error: it is reported per instance in `status` (IPOPT ApplicationReturnStatus
+ * numbering), like the reference, which only exposes it through stats()['success'] (optimizer.py:778).
+ * Threading: one solver handle may be used by one host thread at a time; calls are blocking unless a
+ * stream is given to dmb_solve_device.
+ */
+#ifndef DOMPC_B200_H
+#define DOMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_ABI_VERSION 1
+
+#define DMB_E_OK 0
+#define DMB_E_CUDA (-1)        /* a CUDA runtime call failed; see dmb_last_error */
+#define DMB_E_ARG (-2)         /* invalid argument (null pointer, batch <= 0, wrong option struct size) */
+#define DMB_E_NO_DEVICE (-3)   /* no usable sm_100 device */
+#define DMB_E_STATE (-4)       /* bounds not set before solve */
+
+/* indices into the array filled by dmb_get_dims */
+enum { DMB_DIM_NW = 0, DMB_DIM_NG, DMB_DIM_NP, DMB_DIM_NX, DMB_DIM_NU, DMB_DIM_NZ, DMB_DIM_NAUX, DMB_DIM_NHOR,
+       DMB_DIM_NSCEN, DMB_DIM_NEDGE, DMB_DIM_NNODE, DMB_DIM_OPTSIZE, DMB_DIM_THREADS, DMB_DIM_SMEM, DMB_DIM_WS_DOUBLES,
+       DMB_DIM_COUNT };
+
+/* per-instance statistics written by the solve calls: stats[b*DMB_NSTAT + k] */
+enum { DMB_STAT_MU = 0, DMB_STAT_INF_PR, DMB_STAT_INF_DU, DMB_STAT_OBJ_SCALE, DMB_NSTAT };
+
+typedef struct dmb_solver dmb_solver;
+struct DmbOptions;   /* layout: do_mpc_b200/csrc/ipm_core.cuh, mirrored by do_mpc_b200/solver/options.py */
+
+int dmb_abi_version(void);
+void dmb_get_dims(int* dims /* [DMB_DIM_COUNT] */);
+void dmb_default_options(struct DmbOptions* opts);
+
+dmb_solver* dmb_create(int device);
+void dmb_destroy(dmb_solver* s);
+const char* dmb_last_error(dmb_solver* s);
+
+int dmb_set_options(dmb_solver* s, const struct DmbOptions* opts, int opts_size);
+int dmb_set_bounds(dmb_solver* s, const double* lbx, const double* ubx /* host, n_w each, +-inf allowed */);
+
+/* Initial guess: either x_init [B, n_w] (scaled opt_x, as MPC.opt_x_num) or, when x_init is NULL, the
+ * broadcast of x0s [B,n_x], u0s [B,n_u], z0s [B,n_z] (scaled) that MPC.set_initial_guess() performs
+ * (do_mpc/controller/_mpc.py:969-971).  Outputs x, lam_g, lam_x, g, stats may be NULL. */
+int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double* d_x0s, const double* d_u0s,
+                     const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x, double* d_g,
+                     double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* cuda_stream);
+
+int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s,
+                   const double* p, double* x, double* lam_g, double* lam_x, double* g, double* f, int* status,
+                   int* iters, double* u0, double* stats);
+
+/* aux expressions at every (k, scenario): aux [B, n_horizon * n_scenarios * n_aux] from x [B,n_w], p [B,n_p] (host) */
+int dmb_aux_host(dmb_solver* s, int B, const double* x, const double* p, double* aux);
+
+/* launch geometry of the last solve and number of kernel launches issued by this handle so far */
+int dmb_get_stats(dmb_solver* s, int* grid, int* block, int* smem_bytes, long long* n_launches, float* last_kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

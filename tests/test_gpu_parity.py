@@ -1,0 +1,102 @@
+"""Parity of the CUDA path (through the C-ABI / ctypes, no CPU fallback) with the reference's IPOPT results and
+the oracle.  Tolerances (BASELINE.json north_star / SURVEY.md §8c): own scaled KKT residuals <= 1e-8,
+|u0 - u0_ref| <= 1e-5 * u_scaling on instances where the reference succeeded; success flags must agree."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mpc():
+    import cstr
+    return cstr.cstr_nominal_mpc()
+
+
+def test_dataset_parity_through_cabi(mpc, dataset):
+    out = mpc.make_step_batch(dataset["x0"], dataset["u_prev"])
+    ok_ref = dataset["success"].astype(bool)
+    assert np.array_equal(out["success"], ok_ref), "success split differs from the reference's 692/308"
+    dev = np.abs(out["u0"][ok_ref] - dataset["u0"][ok_ref]) / mpc.recipe.u_scaling
+    assert dev.max() < 1e-5
+    assert np.abs(out["iter_count"][ok_ref] - dataset["iter_count"][ok_ref]).max() <= 1
+    info = mpc.S.launch_info()
+    assert info["n_launches"] >= 1 and info["grid"] >= 1
+
+
+def test_full_solution_kkt_and_oracle(mpc, dataset):
+    from oracle import models
+    from oracle.ipm import IPMSolver, IpmOptions, solve_mpc
+    from oracle.nlp import FlatNLP
+    nlp = FlatNLP(models.cstr_nominal())
+    used = nlp.used_mask()
+    idx = np.where(dataset["success"])[0][:6]
+    out = mpc.make_step_batch(dataset["x0"][idx], dataset["u_prev"][idx], return_full=True)
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300, max_soc=0))
+    for b, i in enumerate(idx):
+        p = nlp.pack_p(dataset["x0"][i], dataset["u_prev"][i])
+        x, lam_g, lam_x = out["x"][b], out["lam_g"][b], out["lam_x"][b]
+        assert np.abs(nlp.g(x, p)).max() < 1e-8                              # primal infeasibility
+        stat = nlp.grad_f(x, p) + nlp.jac_g(x, p).T @ lam_g + lam_x
+        assert np.abs(stat[used]).max() < 1e-7                                  # dual infeasibility
+        r = solve_mpc(nlp, dataset["x0"][i], dataset["u_prev"][i], solver=orc)
+        assert r["iter_count"] == out["iter_count"][b]
+        assert np.abs(r["x"][used] - x[used]).max() < 1e-8
+        # unused reference variables keep the initial guess, like set_initial_guess leaves them
+        w0 = nlp.initial_guess(dataset["x0"][i], dataset["u_prev"][i])
+        assert np.array_equal(x[~used], w0[~used])
+
+
+def test_nlpsol_call_signature_and_make_step(mpc, dataset):
+    i = 0
+    mpc.reset_history()
+    mpc.x0 = dataset["x0"][i]; mpc.u0 = dataset["u_prev"][i]
+    mpc.set_initial_guess()
+    u0 = mpc.make_step(dataset["x0"][i].reshape(-1, 1))
+    assert u0.shape == (2, 1)
+    assert np.abs(u0.ravel() - dataset["u0"][i]).max() / 2000 < 1e-5
+    st = mpc.S.stats()
+    assert st["success"] is True and st["iter_count"] == dataset["iter_count"][i] and st["return_status"] == "Solve_Succeeded"
+    assert mpc.data["_u"].shape == (1, 2) and mpc.data["_opt_x_num"].shape == (1, 376) and mpc.data["_lam_g_num"].shape == (1, 324)
+    # second step warm-starts from the previous solution (reference optimizer.py:741-742)
+    u1 = mpc.make_step(dataset["x0"][i].reshape(-1, 1))
+    assert mpc.S.stats()["success"] and np.isfinite(u1).all()
+    # error behaviour: shape mismatch raises, solver failure does not
+    with pytest.raises(Exception):
+        mpc.make_step(np.zeros((3, 1)))
+
+
+def test_batch_4096_properties(mpc, dataset):
+    """BASELINE config #2 size: independence from batch position, permutation invariance, per-instance KKT stats."""
+    rng = np.random.RandomState(42)
+    B = 4096
+    x0 = rng.uniform([0.1, 0.1, 50, 50], [2, 2, 140, 140], size=(B, 4))
+    up = rng.uniform([5, -8500], [100, 0], size=(B, 2))
+    x0[:1000], up[:1000] = dataset["x0"], dataset["u_prev"]
+    a = mpc.make_step_batch(x0, up)
+    assert np.array_equal(a["success"][:1000], dataset["success"].astype(bool))
+    perm = rng.permutation(B)
+    b = mpc.make_step_batch(x0[perm], up[perm])
+    assert np.array_equal(b["status"], a["status"][perm])
+    assert np.array_equal(b["iter_count"], a["iter_count"][perm])
+    assert np.array_equal(b["u0"], a["u0"][perm]), "results must not depend on the position in the batch"
+    ok = a["success"]
+    assert 0.55 < ok.mean() < 0.85                        # reference: 69.2 % of random starts are feasible
+    st = a["stats"]
+    assert st[ok, 1].max() <= 1e-8 and np.all(st[ok, 0] <= 1e-8)      # inf_pr, final mu
+    lo, hi = np.array([5, -8500.0]), np.array([100, 0.0])
+    assert np.all(a["u0"][ok] >= lo - 1e-4 * np.abs(lo) - 1e-6) and np.all(a["u0"][ok] <= hi + 1e-4)
+
+
+def test_device_resident_api_matches_host_api(mpc, dataset):
+    import torch
+    r = mpc.recipe
+    n = 256
+    P = np.zeros((n, r.n_p)); P[:, :4] = dataset["x0"][:n]; P[:, 4:6] = dataset["u_prev"][:n]
+    host = mpc.S.solve_batch(P, dataset["x0"][:n] / r.x_scaling, dataset["u_prev"][:n] / r.u_scaling,
+                             lbx=mpc._lb_opt_x.full().ravel(), ubx=mpc._ub_opt_x.full().ravel())
+    dev = mpc.S.solve_batch_device(torch.tensor(P, device="cuda"), torch.tensor(dataset["x0"][:n] / r.x_scaling, device="cuda"),
+                                   torch.tensor(dataset["u_prev"][:n] / r.u_scaling, device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["status"].cpu().numpy(), host["status"])
+    assert np.array_equal(dev["u0_scaled"].cpu().numpy(), host["u0_scaled"])
