@@ -126,7 +126,7 @@ def run_reference(args):
     B = args.batch
     x0, up = make_inputs(B, 0)
     cp = CpuPool(x0, up)
-    n_sample = max(cp.cores, min(8 * cp.cores, 256))
+    n_sample = max(cp.cores, min(4 * cp.cores, 512))
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, succ = cp.run(n_sample)
@@ -168,7 +168,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cp = CpuPool(x0, up)
         cores = cp.cores
-        n_sample = max(cores, min(4 * cores, 128))
+        n_sample = max(cores, min(4 * cores, 512))
         v, dt, succ = cp.run(n_sample)
         cp.close()
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
