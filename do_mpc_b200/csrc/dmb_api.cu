@@ -16,16 +16,22 @@
 #define DMB_VEC_SMEM 1
 #endif
 #define DMB_NWARP (DMB_THREADS / 32)
+#define DMB_NGRP (DMB_THREADS / GSZ)
+#ifndef DMB_MIN_CTAS
+#define DMB_MIN_CTAS 1
+#endif
 
 // ---- shared memory carve-up (doubles first, then the small struct) ----------------------------------------
+// tiles of the lane groups | Riccati scratch | per-edge reduced blocks | per-node data | iterate vectors (optional)
 #define SM_TILE 0
-#define SM_HQ (SM_TILE + DMB_NWARP * NY * TILE_LD)
-#define SM_QS (SM_HQ + DMB_NWARP * NQ * HQ_LD)
-#define SM_VEC (SM_QS + DMB_QS_SIZE)
+#define SM_QS (SM_TILE + DMB_NGRP * TILE_SZ)
+#define SM_ER (SM_QS + DMB_QS_SIZE)
+#define SM_NODE (SM_ER + NEDGE * ER_SZ)
+#define SM_VEC (SM_NODE + NNODE * WN_NODE)
 #define SM_DOUBLES (SM_VEC + (DMB_VEC_SMEM ? WV_END : 0))
 #define SM_BYTES (SM_DOUBLES * sizeof(double) + sizeof(DmbShared) + 16)
-// per-CTA global workspace slot
-#define SLOT_DOUBLES ((DMB_VEC_SMEM ? 0 : WV_END) + NEDGE * WS_EDGE + NNODE * WN_NODE)
+// per-CTA global workspace slot: bulk per-edge data (+ the iterate vectors when they do not fit on chip)
+#define SLOT_DOUBLES ((DMB_VEC_SMEM ? 0 : WV_END) + NEDGE * EB_SZ)
 
 struct KernelArgs {
   int B;
@@ -35,16 +41,18 @@ struct KernelArgs {
   DmbOptions o;
 };
 
-__global__ void __launch_bounds__(DMB_THREADS) dmb_solve_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   DmbShared* S = reinterpret_cast<DmbShared*>(sm + SM_DOUBLES);
   __shared__ int cur;
   __shared__ DmbResult result;
-  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5)};
+  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
+        (int)(threadIdx.x % GSZ), (int)(threadIdx.x / GSZ), (int)(blockDim.x / GSZ)};
   double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
   Inst I;
-  bind_instance(I, DMB_VEC_SMEM ? sm + SM_VEC : slot, slot + (DMB_VEC_SMEM ? 0 : WV_END));
+  bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot);
+  I.er = sm + SM_ER; I.node = sm + SM_NODE; I.eb = slot + (DMB_VEC_SMEM ? 0 : WV_END);
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0;
   I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
   while (true) {
@@ -56,7 +64,7 @@ __global__ void __launch_bounds__(DMB_THREADS) dmb_solve_kernel(const KernelArgs
     I.p = a.p + (size_t)b * DMB_NP;
     load_initial_guess(c, a.x_init ? a.x_init + (size_t)b * DMB_NW : nullptr, a.x0s ? a.x0s + (size_t)b * NX : nullptr,
                        a.u0s ? a.u0s + (size_t)b * NU : nullptr, a.z0s ? a.z0s + (size_t)b * DMB_NZ : nullptr, I.wt);
-    solve_instance(c, I, a.o, I.wt, sm + SM_TILE, sm + SM_HQ, sm + SM_QS, S, &result);
+    solve_instance(c, I, a.o, I.wt, sm + SM_TILE, sm + SM_QS, S, &result);
     const double df = result.df;
     if (a.x && a.x_init)
       for (int i = c.tid; i < DMB_NW; i += c.nthr) a.x[(size_t)b * DMB_NW + i] = a.x_init[(size_t)b * DMB_NW + i];

@@ -1,4 +1,4 @@
-// Batched primal-dual interior-point solver for stage-structured collocation NLPs (sm_100a).
+// Batched primal-dual interior-point solver for stage-structured collocation NLPs (sm_100a) — core phases.
 //
 // Replaces the CasADi nlpsol('ipopt') call of the reference (do_mpc/controller/_mpc.py:1328,
 // do_mpc/optimizer.py:770) for a BATCH of problem instances.  One CTA solves one instance at a time
@@ -7,12 +7,18 @@
 // The KKT system of every iteration is solved by a structure-exploiting elimination instead of a
 // sparse LDL^T (MUMPS in the reference):
 //   per edge  : LU of the square collocation block G_y, sensitivities Y = -G_y^{-1} G_v (null-space
-//               projection of the edge Hessian onto the node variables),
+//               projection of the edge Hessian onto the node variables)      -> one lane GROUP per edge,
 //   per node  : Riccati / dynamic-programming sweep over the scenario tree in the augmented state
 //               xi = (x, u_prev); positive definiteness of every control block == correct inertia,
 //   recovery  : forward roll-out, then multipliers by a transposed LU solve per edge.
-// All problem dimensions are compile-time constants from the generated header (problem_gen.h), the
+// All problem dimensions are compile-time constants from the generated header (problem_gen.h); the
 // model functions (residuals, Jacobian / Lagrangian-Hessian nonzeros) are generated straight-line code.
+//
+// Memory plan (v2, after ncu capture r1a showed the kernel bound by dependent L1/L2 round trips in
+// single-thread sections): everything that sits on a dependency chain lives in shared memory
+// (iterates, per-edge reduced blocks, per-node Riccati data, LU tiles); bulk per-edge data that is
+// written once and read once per iteration (LU factors, Y, nonzeros) goes to a per-CTA global slot
+// and is only accessed with group-wide coalesced loops.
 //
 // The file compiles for the device (nvcc) and, with DMB_HOSTSIM, as plain single-thread C++ so that
 // the numerics can be checked on a machine without a GPU (tests/hostsim; never part of the product).
@@ -20,16 +26,16 @@
 #include <math.h>
 #include <stdint.h>
 
+struct Ctx { int tid, nthr, lane, warp, nwarp, gl, grp, ngrp; };
+
 #ifdef DMB_HOSTSIM
 #define DMB_DEV
 #define DMB_LANES 1
-struct Ctx { int tid, nthr, lane, warp, nwarp; };
 #define CTA_SYNC() ((void)0)
 #define WARP_SYNC() ((void)0)
 #else
 #define DMB_DEV __device__ __forceinline__
 #define DMB_LANES 32
-struct Ctx { int tid, nthr, lane, warp, nwarp; };
 #define CTA_SYNC() __syncthreads()
 #define WARP_SYNC() __syncwarp()
 #endif
@@ -59,7 +65,7 @@ enum DmbStatus {
 #include "problem_gen.h"   // generated: dimensions, tables, model functions
 
 // ---------------------------------------------------------------------------------------------------
-// derived dimensions and internal layouts
+// derived dimensions and layouts
 // ---------------------------------------------------------------------------------------------------
 #define NX DMB_NX
 #define NU DMB_NU
@@ -71,6 +77,7 @@ enum DmbStatus {
 #define NXI (NX + NU)                 // augmented Riccati state (x, u_prev)
 #define NUT (NU + NEPS)               // stage controls (u, eps)
 #define NV (NXI + NUT)                // (x, u_prev, u, eps)
+#define NE (NVP + 1)                  // extended right-hand sides [G_vp | rhs]
 #define NNODE DMB_NNODE
 #define NEDGE DMB_NEDGE
 #define NHOR DMB_NHOR
@@ -80,45 +87,60 @@ enum DmbStatus {
 #define NLE (NY + NX + NNL)                           // multipliers per edge: lamG | lamC | y_d
 #define NLAM (NX + NEDGE * NLE)
 #define LAM_EDGE(e) (NX + (e) * NLE)
-#define TILE_NC (NY + NVP + 1)                        // [G_y | G_vp | rhs] take part in the elimination
-#define TILE_M (TILE_NC)                              // then NVP scratch columns for M = H_yy Y
-#define TILE_LD ((TILE_NC + NVP) | 1)                 // odd leading dimension: conflict-free 64-bit rows
-#define HQ_LD ((NQ) | 1)
 #define DMB_INF 1e19
 #define MAX_FILTER 64
 
-// per-edge persistent workspace (doubles)
-#define WS_LU 0
-#define WS_Y (WS_LU + NY * NY)                          // Y (NY x NVP), row-major
-#define WS_Y0 (WS_Y + NY * NVP)                         // y0 (NY)
-#define WS_HNZ (WS_Y0 + NY)
-#define WS_DNZ (WS_HNZ + DMB_NNZ_H)
-#define WS_HHAT (WS_DNZ + DMB_NNZ_D)                    // T'HT without regularisation (NVP x NVP)
-#define WS_YTY (WS_HHAT + NVP * NVP)                    // Y'Y
-#define WS_GHAT (WS_YTY + NVP * NVP)                    // reduced gradient (NVP)
-#define WS_YTY0 (WS_GHAT + NVP)                         // Y'y0
-#define WS_B (WS_YTY0 + NVP)                            // b (NX)
-#define WS_GQ (WS_B + NX)                               // barrier-objective gradient wrt q (NQ)
-#define WS_SIGY (WS_GQ + NQ)                            // Sigma on y (NY)
-#define WS_SIGS (WS_SIGY + NY)                          // Sigma on inequality slacks (NNL)
-#define WS_RD (WS_SIGS + NNL)                           // condensed inequality rhs (NNL)
-#define WS_TMP (WS_RD + NNL)                            // scratch (NQ)
-#define WS_PIV (WS_TMP + NQ)                            // pivots stored as doubles (NY)
-#define WS_EDGE (WS_PIV + NY)
-// per-node persistent workspace
+// lane groups: one group factorises one edge
+#ifdef DMB_HOSTSIM
+#define GSZ 1
+#else
+#define GSZ (NY <= 16 ? 16 : 32)
+#endif
+// LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], then NVP rows of N = H_vy*Yext
+#define TILE_NC (NY + NE)
+#define TILE_M (NY + NE)
+#define TILE_LD ((NY + 2 * NE) | 1)                   // odd leading dimension: conflict-free 64-bit rows
+#define TILE_ROWS (NY + NVP)
+#define TILE_SZ (TILE_ROWS * TILE_LD)
+
+// per-edge reduced data kept in shared memory (inputs of the Riccati sweep)
+#define ER_AB 0                                        // Y[xf rows] : NX x NVP
+#define ER_B (ER_AB + NX * NVP)                        // b (NX)
+#define ER_HH (ER_B + NX)                              // T'HT without delta (NVP x NVP)
+#define ER_YTY (ER_HH + NVP * NVP)                     // Y'Y
+#define ER_GH (ER_YTY + NVP * NVP)                     // reduced gradient (NVP)
+#define ER_YTY0 (ER_GH + NVP)                          // Y'y0
+#define ER_SZ (ER_YTY0 + NVP)
+// per-edge bulk data in the per-CTA global slot (coalesced group access only)
+#define EB_LU 0
+#define EB_PIV (EB_LU + NY * NY)
+#define EB_Y (EB_PIV + NY)                             // Yext = [Y | y0], NY x NE row-major
+#define EB_JNZ (EB_Y + NY * NE)
+#define EB_HNZ (EB_JNZ + DMB_NNZ_J)
+#define EB_DNZ (EB_HNZ + DMB_NNZ_H)                    // scaled inequality Jacobian nonzeros
+#define EB_GOBJ (EB_DNZ + DMB_NNZ_D)                   // edge-local objective gradient wrt q (NQ)
+#define EB_GCON (EB_GOBJ + NQ)                         // edge-local constraint part of grad L wrt q (NQ)
+#define EB_GY (EB_GCON + NQ)                           // total barrier-objective gradient of y (NY)
+#define EB_SIGY (EB_GY + NY)
+#define EB_SIGS (EB_SIGY + NY)
+#define EB_RD (EB_SIGS + NNL)
+#define EB_SZ (EB_RD + NNL)
+// per-node data in shared memory
 #define WN_P 0                                          // P (NXI x NXI)
 #define WN_PV (WN_P + NXI * NXI)                        // p (NXI)
 #define WN_K (WN_PV + NXI)                              // K (NUT x NXI)
 #define WN_KV (WN_K + NUT * NXI)                        // k (NUT)
 #define WN_DXI (WN_KV + NUT)                            // d xi (NXI)
 #define WN_NODE (WN_DXI + NXI)
-// vectors
+// iterate vectors
 #define WV_W 0
 #define WV_WT (WV_W + NWI)
 #define WV_DW (WV_WT + NWI)
 #define WV_ZL (WV_DW + NWI)
 #define WV_ZU (WV_ZL + NWI)
-#define WV_LAM (WV_ZU + NWI)
+#define WV_GL (WV_ZU + NWI)                              // grad of Lagrangian without bound multipliers
+#define WV_GO (WV_GL + NWI)                              // objective gradient
+#define WV_LAM (WV_GO + NWI)
 #define WV_LAMN (WV_LAM + NLAM)
 #define WV_RES (WV_LAMN + NLAM)                          // residuals, same layout as lam
 #define WV_REST (WV_RES + NLAM)
@@ -127,21 +149,22 @@ enum DmbStatus {
 #define WV_ST (WV_S + NEDGE * NNL)
 #define WV_DS (WV_ST + NEDGE * NNL)
 #define WV_VU (WV_DS + NEDGE * NNL)
-#define WV_GL (WV_VU + NEDGE * NNL)                      // gradient scratch (NWI)
-#define WV_END (WV_GL + NWI)
-#define WS_TOTAL (WV_END + NEDGE * WS_EDGE + NNODE * WN_NODE)
+#define WV_END (WV_VU + NEDGE * NNL)
+#define DMB_QS_SIZE (NV * NV + NV + NXI * NV + 8)
 
 struct Inst {
-  double *w, *wt, *dw, *zL, *zU, *lam, *lamn, *res, *rest, *dc, *s, *st, *ds, *vU, *gl;
-  double *edge, *node;
+  double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *res, *rest, *dc, *s, *st, *ds, *vU;
+  double *er, *node, *eb;
   const double *p, *lb, *ub;
   double df, relax_fac, relax_max;
 };
+DMB_DEV void bind_vectors(Inst& I, double* vec) {
+  I.w = vec + WV_W; I.wt = vec + WV_WT; I.dw = vec + WV_DW; I.zL = vec + WV_ZL; I.zU = vec + WV_ZU;
+  I.gl = vec + WV_GL; I.go = vec + WV_GO;
+  I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
+  I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU;
+}
 DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + k * DMB_NTVP; }
-#if DMB_NNL > 0
-// relaxed upper bound of the (scaled) inequality row i of edge e (IPOPT bound_relax_factor)
-#define DMB_NL_UB_RELAXED(I, e, i) nl_ub_relaxed(I, e, i)
-#endif
 
 // ---------------------------------------------------------------------------------------------------
 // reductions
@@ -150,21 +173,13 @@ DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + 
 static inline double block_sum(const Ctx&, double v, double*) { return v; }
 static inline double block_max(const Ctx&, double v, double*) { return v; }
 static inline double block_min(const Ctx&, double v, double*) { return v; }
+static inline int group_argmax(const Ctx&, double, int idx) { return idx; }
 #else
 #define DMB_FULL 0xffffffffu
-DMB_DEV double warp_sum(double v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DMB_FULL, v, o);
-  return v;
-}
-DMB_DEV double warp_max(double v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(DMB_FULL, v, o));
-  return v;
-}
-DMB_DEV double warp_min(double v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(DMB_FULL, v, o));
-  return v;
-}
-// scratch: >= 32 doubles of shared memory; result broadcast to all threads
+DMB_DEV double warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DMB_FULL, v, o); return v; }
+DMB_DEV double warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(DMB_FULL, v, o)); return v; }
+DMB_DEV double warp_min(double v) { for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(DMB_FULL, v, o)); return v; }
+// scratch: >= 2*nwarp doubles of shared memory (double-buffered by call parity); result broadcast to all threads
 DMB_DEV double block_sum(const Ctx& c, double v, double* scratch) {
   v = warp_sum(v);
   CTA_SYNC();
@@ -192,6 +207,14 @@ DMB_DEV double block_min(const Ctx& c, double v, double* scratch) {
   for (int i = 1; i < c.nwarp; ++i) r = fmin(r, scratch[i]);
   return r;
 }
+// index of the largest |val| among the lanes of a group (idx < 64, idx < 0 = no candidate): one REDUX on packed keys
+DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
+  unsigned key = 0u;
+  if (idx >= 0) key = ((__float_as_uint((float)fabs(val)) & 0x7fffffc0u) | (unsigned)(63 - idx)) + 64u;
+  const unsigned mask = GSZ == 32 ? DMB_FULL : (0xffffu << (c.lane & 16));
+  const unsigned best = __reduce_max_sync(mask, key);
+  return 63 - (int)((best - 64u) & 63u);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------------
@@ -216,6 +239,7 @@ DMB_DEV double node_uprev(const Inst& I, const double* w, int n, int i) {
 }
 
 #if DMB_NNL > 0
+// relaxed upper bound of the (scaled) inequality row i of edge e (IPOPT bound_relax_factor)
 DMB_DEV double nl_ub_relaxed(const Inst& I, int e, int i) {
   const double u = I.dc[LAM_EDGE(e) + NY + NX + i] * DMB_NL_UB[i];
   return u + fmin(I.relax_fac * fmax(1.0, fabs(u)), I.relax_max);
@@ -223,8 +247,8 @@ DMB_DEV double nl_ub_relaxed(const Inst& I, int e, int i) {
 #endif
 
 // ---------------------------------------------------------------------------------------------------
-// residuals + objective at a point (w, s) -> res (scaled), returns objective (scaled by df) through *f_out
-// theta = 1-norm of the residual vector.  All threads of the CTA participate.
+// residuals + objective at a point (w, s) -> res (scaled), objective (scaled by df), theta = ||res||_1.
+// One thread per edge for the generated code; all threads for the reductions.
 // ---------------------------------------------------------------------------------------------------
 DMB_DEV void eval_point(const Ctx& c, const Inst& I, const double* w, const double* s, double* res,
                         double* scratch, double* f_out, double* theta_out, double* infpr_out) {
@@ -270,337 +294,264 @@ DMB_DEV void eval_point(const Ctx& c, const Inst& I, const double* w, const doub
 }
 
 // ---------------------------------------------------------------------------------------------------
-// gradient of  sig*f + lam'c  w.r.t. all primal variables into gl (NWI).  with_lam=0 -> objective only.
-// lam are the SCALED multipliers; row scales dc are applied here.  Uses per-edge scratch WS_TMP.
+// all derivatives at the current point, once per iteration: per edge (one thread each, fused generated
+// code) Jacobian / Hessian nonzeros and gradients into the bulk slot; then the gradients of the
+// objective (go) and of the Lagrangian without bound multipliers (gl) for every primal variable.
+// lam are the SCALED multipliers; the row scales dc are applied here.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void eval_gradient(const Ctx& c, const Inst& I, const double* w, const double* lam, int with_lam, double* gl) {
+DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
+  const double* w = I.w;
   for (int e = c.tid; e < NEDGE; e += c.nthr) {
-    double q[NQ], lg[NY > 0 ? NY : 1], ln[NNL > 0 ? NNL : 1], gq[NQ];
+    double q[NQ], lg[NY > 0 ? NY : 1], ln[NNL > 0 ? NNL : 1];
     gather_q(w, e, q);
     const double* dc = I.dc + LAM_EDGE(e);
-    const double* le = lam + LAM_EDGE(e);
+    const double* le = I.lam + LAM_EDGE(e);
 #pragma unroll
-    for (int i = 0; i < NY; ++i) lg[i] = with_lam ? dc[i] * le[i] : 0.0;
+    for (int i = 0; i < NY; ++i) lg[i] = dc[i] * le[i];
 #pragma unroll
-    for (int i = 0; i < NNL; ++i) ln[i] = with_lam ? dc[NY + NX + i] * le[NY + NX + i] : 0.0;
-    gen_lag_grad(q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln, gq);
-    if (with_lam) {
+    for (int i = 0; i < NNL; ++i) ln[i] = dc[NY + NX + i] * le[NY + NX + i];
+    double* eb = I.eb + (size_t)e * EB_SZ;
+    gen_derivs(q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln,
+               eb + EB_GOBJ, eb + EB_GCON, eb + EB_JNZ, eb + EB_HNZ, eb + EB_DNZ);
+    // continuity multiplier on the end-of-interval state, inequality Jacobian scaling
 #pragma unroll
-      for (int i = 0; i < NX; ++i) gq[NVP + DMB_XF_SEL[i]] += le[NY + i];
-    }
-    double* t = I.edge + e * WS_EDGE + WS_TMP;
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) t[i] = gq[i];
+    for (int i = 0; i < NX; ++i) eb[EB_GCON + NVP + DMB_XF_SEL[i]] += le[NY + i];
+#if NNL > 0
+    for (int k = 0; k < DMB_NNZ_D; ++k) eb[EB_DNZ + k] *= dc[NY + NX + DMB_D_ROW[k]];
+#endif
   }
   CTA_SYNC();
   // node variables: sum over child edges (+ continuity of the parent edge, terminal cost, rterm)
   for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
     const int n = idx / NVP, i = idx - n * NVP;
     const int k = DMB_NODE_K[n];
-    double g = 0.0;
+    double go = 0.0, gc = 0.0;
     if (k < NHOR) {
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) g += I.edge[(DMB_NODE_FIRST_EDGE[n] + j) * WS_EDGE + WS_TMP + i];
-    } else if (i >= NX) { gl[idx] = 0.0; continue; }
+      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+        const double* eb = I.eb + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ;
+        go += eb[EB_GOBJ + i]; gc += eb[EB_GCON + i];
+      }
+    } else if (i >= NX) { I.gl[idx] = 0.0; I.go[idx] = 0.0; continue; }
     if (i < NX) {
       const int pe = DMB_NODE_PARENT_EDGE[n];
       if (pe >= 0) {
-        if (with_lam) g -= lam[LAM_EDGE(pe) + NY + i];
+        gc -= I.lam[LAM_EDGE(pe) + NY + i];
         if (k == NHOR) {
           double gm[NX];
           gen_mterm_grad(w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm);
-          g += I.df * DMB_EDGE_OMEGA[pe] * gm[i];
+          go += I.df * DMB_EDGE_OMEGA[pe] * gm[i];
         }
-      } else if (with_lam) g += lam[i];
+      } else gc += I.lam[i];
     } else if (i < NX + NU) {
       const int iu = i - NX;
       double up[NU], gr[2 * NU];
 #pragma unroll
       for (int a = 0; a < NU; ++a) up[a] = node_uprev(I, w, n, a);
       gen_rterm_grad(w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + k * DMB_NTVP, gr);
-      g += I.df * DMB_NODE_RW[n] * gr[iu];
+      go += I.df * DMB_NODE_RW[n] * gr[iu];
       // this node's input is u_prev of every child node that still has a control
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int cn = DMB_EDGE_CHILD[DMB_NODE_FIRST_EDGE[n] + j];
         if (DMB_NODE_K[cn] == NHOR) continue;
         gen_rterm_grad(w + NODE_OFF(cn) + NX, w + NODE_OFF(n) + NX, I.p + DMB_P_TVP + (k + 1) * DMB_NTVP, gr);
-        g += I.df * DMB_NODE_RW[cn] * gr[NU + iu];
+        go += I.df * DMB_NODE_RW[cn] * gr[NU + iu];
       }
     }
-    gl[idx] = g;
+    I.go[idx] = go; I.gl[idx] = go + gc;
   }
   for (int idx = c.tid; idx < NEDGE * NY; idx += c.nthr) {
     const int e = idx / NY, i = idx - e * NY;
-    gl[NNODE * NVP + idx] = I.edge[e * WS_EDGE + WS_TMP + NVP + i];
+    const double* eb = I.eb + (size_t)e * EB_SZ;
+    const double go = eb[EB_GOBJ + NVP + i];
+    I.go[NNODE * NVP + idx] = go; I.gl[NNODE * NVP + idx] = go + eb[EB_GCON + NVP + i];
   }
   CTA_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------------
-// H_e * v for the edge Hessian (Lagrangian nonzeros + inequality condensation + Sigma_y + delta on y)
-// serial, one thread.  hv and v have NQ entries.
+// factor phase.  One lane group per edge: assemble [G_y | G_vp | -res] from the Jacobian nonzeros,
+// LU with partial pivoting (REDUX pivot search), Yext = [Y | y0] by back substitution (one lane per
+// right-hand side), sparse Hessian products M = (H_yy+Sigma_y) Yext, N = H_vy Yext, and the reduced
+// blocks for the Riccati sweep.  `res` supplies the right-hand side (ignored in ls_mode: zero).
+// ls_mode = least-squares multiplier estimate: Hessian := identity, gradient := grad f - zL + zU.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void edge_hmul(const double* we, double delta, const double* v, double* hv) {
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) hv[i] = 0.0;
-  const double* hnz = we + WS_HNZ;
-  for (int k = 0; k < DMB_NNZ_H; ++k) {
-    const int r = DMB_H_ROW[k], cc = DMB_H_COL[k];
-    const double a = hnz[k];
-    hv[r] += a * v[cc];
-    if (r != cc) hv[cc] += a * v[r];
-  }
-#if NNL > 0
-  double jd[NNL];
-  for (int i = 0; i < NNL; ++i) jd[i] = 0.0;
-  for (int k = 0; k < DMB_NNZ_D; ++k) jd[DMB_D_ROW[k]] += we[WS_DNZ + k] * v[DMB_D_COL[k]];
-  for (int i = 0; i < NNL; ++i) jd[i] *= we[WS_SIGS + i];
-  for (int k = 0; k < DMB_NNZ_D; ++k) hv[DMB_D_COL[k]] += we[WS_DNZ + k] * jd[DMB_D_ROW[k]];
-#endif
-  for (int i = 0; i < NY; ++i) hv[NVP + i] += (we[WS_SIGY + i] + delta) * v[NVP + i];
-}
-
-// solve G_y x = b with the stored LU (row swaps as recorded), in place.  One thread.
-DMB_DEV void lu_solve(const double* we, double* b) {
-  const double* LU = we + WS_LU;
-  for (int k = 0; k < NY; ++k) {
-    const int pr = (int)we[WS_PIV + k];
-    if (pr != k) { const double t = b[k]; b[k] = b[pr]; b[pr] = t; }
-  }
-  for (int k = 0; k < NY; ++k) {
-    const double bk = b[k];
-    for (int r = k + 1; r < NY; ++r) b[r] -= LU[r * NY + k] * bk;
-  }
-  for (int k = NY - 1; k >= 0; --k) {
-    double a = b[k];
-    for (int cc = k + 1; cc < NY; ++cc) a -= LU[k * NY + cc] * b[cc];
-    b[k] = a / LU[k * NY + k];
-  }
-}
-// solve G_y' x = b, in place
-DMB_DEV void lu_solve_t(const double* we, double* b) {
-  const double* LU = we + WS_LU;
-  for (int k = 0; k < NY; ++k) {            // U' a = b
-    double a = b[k];
-    for (int r = 0; r < k; ++r) a -= LU[r * NY + k] * b[r];
-    b[k] = a / LU[k * NY + k];
-  }
-  for (int k = NY - 1; k >= 0; --k) {       // L' c = a (unit diagonal)
-    double a = b[k];
-    for (int r = k + 1; r < NY; ++r) a -= LU[r * NY + k] * b[r];
-    b[k] = a;
-  }
-  for (int k = NY - 1; k >= 0; --k) {
-    const int pr = (int)we[WS_PIV + k];
-    if (pr != k) { const double t = b[k]; b[k] = b[pr]; b[pr] = t; }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// factor phase: per edge Jacobian tile -> LU, Y ; Hessian tile -> projected blocks.  One warp per edge.
-// tile: NY x TILE_LD, hq: NQ x HQ_LD (warp-private shared memory).
-// returns through *fail a nonzero value when a pivot is (numerically) zero.
-// ---------------------------------------------------------------------------------------------------
-DMB_DEV void factor_edges(const Ctx& c, const Inst& I, double mu, double kappa_d, int ls_mode, double* tile_base, double* hq_base, int* fail) {
-  double* T = tile_base + (size_t)c.warp * NY * TILE_LD;
-  double* HQ = hq_base + (size_t)c.warp * NQ * HQ_LD;
-  for (int e = c.warp; e < NEDGE; e += c.nwarp) {
-    double* we = I.edge + (size_t)e * WS_EDGE;
-    const double* tv = edge_tvp(I.p, e);
-    const double* pp = edge_pp(I.p, e);
-    const double* dc = I.dc + LAM_EDGE(e);
-    const double* le = I.lam + LAM_EDGE(e);
-    // -- zero tiles
-    for (int i = c.lane; i < NY * TILE_LD; i += DMB_LANES) T[i] = 0.0;
-    for (int i = c.lane; i < NQ * HQ_LD; i += DMB_LANES) HQ[i] = 0.0;
+DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
+                          double* tile_base, int* fail) {
+  double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
+    const int e = e0 + c.grp;
+    const bool act = e < NEDGE;
+    double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+    double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
+    const double* dc = I.dc + LAM_EDGE(act ? e : 0);
+    if (act) {
+      for (int i = c.gl; i < TILE_SZ; i += GSZ) T[i] = 0.0;
+    }
     WARP_SYNC();
-    // -- model derivatives: straight-line generated code, one lane
-    if (c.lane == 0) {
-      double q[NQ];
-      gather_q(I.w, e, q);
-      {
-        double jnz[DMB_NNZ_J > 0 ? DMB_NNZ_J : 1];
-        gen_J(q, tv, pp, jnz);
-        for (int k = 0; k < DMB_NNZ_J; ++k) {
-          const int r = DMB_J_ROW[k], cq = DMB_J_COL[k];
-          const int col = cq >= NVP ? cq - NVP : NY + cq;      // tile columns: [G_y | G_vp | rhs]
-          T[r * TILE_LD + col] = dc[r] * jnz[k];
-        }
+    if (act) {
+      // Jacobian nonzeros (row scaled) -> tile columns [G_y | G_vp]; right-hand side -res
+      for (int k = c.gl; k < DMB_NNZ_J; k += GSZ) {
+        const int r = DMB_J_ROW[k], cq = DMB_J_COL[k];
+        T[r * TILE_LD + (cq >= NVP ? cq - NVP : NY + cq)] = dc[r] * eb[EB_JNZ + k];
       }
-      {
-        double lg[NY > 0 ? NY : 1], ln[NNL > 0 ? NNL : 1];
-        for (int i = 0; i < NY; ++i) lg[i] = 0.0;
-        for (int i = 0; i < NNL; ++i) ln[i] = 0.0;
-        // edge-local objective gradient (node-level terms are added in the Riccati sweep)
-        gen_lag_grad(q, tv, pp, lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln, we + WS_GQ);
-        if (ls_mode) {
-          for (int k = 0; k < DMB_NNZ_H; ++k) we[WS_HNZ + k] = 0.0;
-        } else {
-          for (int i = 0; i < NY; ++i) lg[i] = dc[i] * le[i];
-          for (int i = 0; i < NNL; ++i) ln[i] = dc[NY + NX + i] * le[NY + NX + i];
-          gen_lag_hess(q, tv, pp, lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln, we + WS_HNZ);
-          for (int k = 0; k < DMB_NNZ_H; ++k) {
-            const int r = DMB_H_ROW[k], cc = DMB_H_COL[k];
-            const double a = we[WS_HNZ + k];
-            HQ[r * HQ_LD + cc] = a; HQ[cc * HQ_LD + r] = a;
-          }
-        }
-      }
-      // barrier terms of the edge unknowns y
-      const double* wy = I.w + EDGE_OFF(e);
-      const double* lb = I.lb + EDGE_OFF(e);
-      const double* ub = I.ub + EDGE_OFF(e);
-      const double* zl = I.zL + EDGE_OFF(e);
-      const double* zu = I.zU + EDGE_OFF(e);
-      for (int i = 0; i < NY; ++i) {
+      for (int r = c.gl; r < NY; r += GSZ) {
+        T[r * TILE_LD + NY + NVP] = ls_mode ? 0.0 : -res[LAM_EDGE(e) + r];
+        // barrier terms of the edge unknowns y
+        const int i = EDGE_OFF(e) + r;
+        const double lo = I.lb[i], hi = I.ub[i], wy = I.w[i];
+        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
         double sig = 0.0, gb = 0.0;
-        const bool hl = lb[i] > -DMB_INF, hu = ub[i] < DMB_INF;
         if (ls_mode) {
           sig = 1.0;
-          if (hl) gb -= zl[i];
-          if (hu) gb += zu[i];
+          if (hl) gb -= I.zL[i];
+          if (hu) gb += I.zU[i];
         } else {
-          if (hl) { const double sl = wy[i] - lb[i]; sig += zl[i] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
-          if (hu) { const double su = ub[i] - wy[i]; sig += zu[i] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
+          if (hl) { const double sl = wy - lo; sig += I.zL[i] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
+          if (hu) { const double su = hi - wy; sig += I.zU[i] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
         }
-        we[WS_SIGY + i] = sig;
-        we[WS_GQ + NVP + i] += gb;
-        HQ[(NVP + i) * HQ_LD + NVP + i] += sig;
+        eb[EB_SIGY + r] = sig;
+        eb[EB_GY + r] = eb[EB_GOBJ + NVP + r] + gb;
       }
 #if NNL > 0
-      {
-        double dnz[DMB_NNZ_D > 0 ? DMB_NNZ_D : 1];
-        gen_nl_jac(q, tv, pp, dnz);
-        for (int k = 0; k < DMB_NNZ_D; ++k) we[WS_DNZ + k] = dc[NY + NX + DMB_D_ROW[k]] * dnz[k];
-        for (int i = 0; i < NNL; ++i) {
-          const double ubs = DMB_NL_UB_RELAXED(I, e, i);
-          const double sl = ubs - I.s[e * NNL + i];
-          const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
-          we[WS_SIGS + i] = sig;
-          // r_d = Sigma_s (d - s) + grad_s phi ; grad_s phi = mu/sl - kappa_d*mu (upper bound only)
-          we[WS_RD + i] = ls_mode ? I.vU[e * NNL + i] : sig * I.res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
-        }
-        for (int k = 0; k < DMB_NNZ_D; ++k) {
-          const int r = DMB_D_ROW[k], cq = DMB_D_COL[k];
-          we[WS_GQ + cq] += we[WS_DNZ + k] * we[WS_RD + r];
-          for (int k2 = 0; k2 < DMB_NNZ_D; ++k2) {
-            if (DMB_D_ROW[k2] != r) continue;
-            HQ[cq * HQ_LD + DMB_D_COL[k2]] += we[WS_DNZ + k] * we[WS_SIGS + r] * we[WS_DNZ + k2];
-          }
-        }
+      for (int i = c.gl; i < NNL; i += GSZ) {
+        const double sl = nl_ub_relaxed(I, e, i) - I.s[e * NNL + i];
+        const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
+        eb[EB_SIGS + i] = sig;
+        // r_d = Sigma_s (d - s) + grad_s phi ; grad_s phi = mu/sl - kappa_d*mu (upper bound only)
+        eb[EB_RD + i] = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
       }
 #endif
     }
     WARP_SYNC();
-    for (int r = c.lane; r < NY; r += DMB_LANES) T[r * TILE_LD + NY + NVP] = ls_mode ? 0.0 : -I.res[LAM_EDGE(e) + r];
-    WARP_SYNC();
-    // -- LU with partial pivoting on columns [0, NY); the other columns ride along
+    // ---- LU with partial pivoting; columns [NY, TILE_NC) ride along -------------------------------------------------
     for (int k = 0; k < NY; ++k) {
-      // pivot search (small: every lane scans; identical result on all lanes)
-      int pr = k; double best = fabs(T[k * TILE_LD + k]);
-      for (int r = k + 1; r < NY; ++r) { const double a = fabs(T[r * TILE_LD + k]); if (a > best) { best = a; pr = r; } }
-      if (!(best > 1e-300)) { *fail = 1; }
-      if (pr != k) {
-        for (int cc = c.lane; cc < TILE_NC; cc += DMB_LANES) {
+      double best = -1.0; int myr = -1;
+      if (act) for (int r = c.gl; r < NY; r += GSZ) if (r >= k) { const double a = fabs(T[r * TILE_LD + k]); if (a > best) { best = a; myr = r; } }
+      const int pr = group_argmax(c, best, myr);
+      if (act && pr != k) {
+        for (int cc = c.gl; cc < TILE_NC; cc += GSZ) {
           const double t = T[k * TILE_LD + cc]; T[k * TILE_LD + cc] = T[pr * TILE_LD + cc]; T[pr * TILE_LD + cc] = t;
         }
       }
-      if (c.lane == 0) we[WS_PIV + k] = (double)pr;
+      if (act && c.gl == 0) eb[EB_PIV + k] = (double)pr;
       WARP_SYNC();
-      const double piv = 1.0 / T[k * TILE_LD + k];
-      WARP_SYNC();
-      for (int r = k + 1 + c.lane; r < NY; r += DMB_LANES) T[r * TILE_LD + k] *= piv;
-      WARP_SYNC();
-      const int nr = NY - k - 1, ncol = TILE_NC - k - 1;
-      for (int idx = c.lane; idx < nr * ncol; idx += DMB_LANES) {
-        const int r = k + 1 + idx / ncol, cc = k + 1 + idx % ncol;
-        T[r * TILE_LD + cc] -= T[r * TILE_LD + k] * T[k * TILE_LD + cc];
+      if (act) {
+        const double pv = T[k * TILE_LD + k];
+        if (!(fabs(pv) > 1e-300)) *fail = 1;
+        const double inv = 1.0 / pv;
+        for (int r = c.gl; r < NY; r += GSZ) if (r > k) {
+          const double l = T[r * TILE_LD + k] * inv;
+          T[r * TILE_LD + k] = l;
+#pragma unroll 4
+          for (int cc = k + 1; cc < TILE_NC; ++cc) T[r * TILE_LD + cc] -= l * T[k * TILE_LD + cc];
+        }
       }
       WARP_SYNC();
     }
-    // store LU
-    for (int idx = c.lane; idx < NY * NY; idx += DMB_LANES) we[WS_LU + idx] = T[(idx / NY) * TILE_LD + idx % NY];
-    // -- back substitution on the right-hand-side columns: U X = (L^-1 P rhs)
-    for (int k = NY - 1; k >= 0; --k) {
-      const double piv = 1.0 / T[k * TILE_LD + k];
-      WARP_SYNC();
-      for (int cc = NY + c.lane; cc < TILE_NC; cc += DMB_LANES) T[k * TILE_LD + cc] *= piv;
-      WARP_SYNC();
-      const int ncol = TILE_NC - NY;
-      for (int idx = c.lane; idx < k * ncol; idx += DMB_LANES) {
-        const int r = idx / ncol, cc = NY + idx % ncol;
-        T[r * TILE_LD + cc] -= T[r * TILE_LD + k] * T[k * TILE_LD + cc];
+    if (act) {
+      for (int idx = c.gl; idx < NY * NY; idx += GSZ) eb[EB_LU + idx] = T[(idx / NY) * TILE_LD + idx % NY];
+      // ---- back substitution, one lane per right-hand side; then Yext = [-X | x_rhs] --------------------------------
+      for (int j = c.gl; j < NE; j += GSZ) {
+        for (int k = NY - 1; k >= 0; --k) {
+          double x = T[k * TILE_LD + NY + j];
+          for (int cc = k + 1; cc < NY; ++cc) x -= T[k * TILE_LD + cc] * T[cc * TILE_LD + NY + j];
+          T[k * TILE_LD + NY + j] = x / T[k * TILE_LD + k];
+        }
+        if (j < NVP) for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = -T[k * TILE_LD + NY + j];
       }
-      WARP_SYNC();
-    }
-    // Y = -X[:, :NVP] ; y0 = X[:, NVP]  (rhs column already holds -res)
-    for (int idx = c.lane; idx < NY * NVP; idx += DMB_LANES) {
-      const int r = idx / NVP, cc = idx - r * NVP;
-      const double y = -T[r * TILE_LD + NY + cc];
-      T[r * TILE_LD + NY + cc] = y;
-      we[WS_Y + idx] = y;
-    }
-    for (int r = c.lane; r < NY; r += DMB_LANES) we[WS_Y0 + r] = T[r * TILE_LD + NY + NVP];
-    WARP_SYNC();
-    // -- projection: M = H_yy Y (into T columns [0,NVP) which are free now) ; Hhat = H_vv + H_vy Y + (H_vy Y)' + Y' M
-    for (int idx = c.lane; idx < NY * NVP; idx += DMB_LANES) {
-      const int r = idx / NVP, cc = idx - r * NVP;
-      double a = 0.0;
-      for (int j = 0; j < NY; ++j) a += HQ[(NVP + r) * HQ_LD + NVP + j] * T[j * TILE_LD + NY + cc];
-      T[r * TILE_LD + TILE_M + cc] = a;
     }
     WARP_SYNC();
-    for (int idx = c.lane; idx < NVP * NVP; idx += DMB_LANES) {
-      const int a = idx / NVP, b = idx - a * NVP;
-      double hvv = HQ[a * HQ_LD + b], yty = 0.0;
-      for (int j = 0; j < NY; ++j) {
-        const double yja = T[j * TILE_LD + NY + a], yjb = T[j * TILE_LD + NY + b];
-        hvv += HQ[a * HQ_LD + NVP + j] * yjb + yja * HQ[(NVP + j) * HQ_LD + b] + yja * T[j * TILE_LD + TILE_M + b];
-        yty += yja * yjb;
+    if (act) {
+      for (int idx = c.gl; idx < NY * NE; idx += GSZ) eb[EB_Y + idx] = T[(idx / NE) * TILE_LD + NY + idx % NE];
+      // ---- M = (H_yy + Sigma_y) Yext  (rows NY, cols NE) and N = H_vy Yext (rows NVP) via the CSR rows of H ----------
+      for (int idx = c.gl; idx < NQ * NE; idx += GSZ) {
+        const int rq = idx / NE, a = idx - rq * NE;            // rq < NVP: N row, else M row
+        double s = 0.0;
+        if (!ls_mode)
+          for (int t = DMB_HR_START[rq]; t < DMB_HR_START[rq + 1]; ++t) {
+            const int cq = DMB_HR_COL[t];
+            if (cq >= NVP) s += eb[EB_HNZ + DMB_HR_IDX[t]] * T[(cq - NVP) * TILE_LD + NY + a];
+          }
+        if (rq >= NVP) {
+          s += eb[EB_SIGY + rq - NVP] * T[(rq - NVP) * TILE_LD + NY + a];
+          T[(rq - NVP) * TILE_LD + TILE_M + a] = s;
+        } else T[(NY + rq) * TILE_LD + a] = s;
       }
-      we[WS_HHAT + idx] = hvv;
-      we[WS_YTY + idx] = yty;
     }
     WARP_SYNC();
-  }
-}
-
-// solve phase per edge (one thread per edge): y0 for the given residuals, reduced gradient, offsets
-DMB_DEV void solve_edges(const Ctx& c, const Inst& I, const double* res, double delta, int recompute_y0) {
-  for (int e = c.tid; e < NEDGE; e += c.nthr) {
-    double* we = I.edge + (size_t)e * WS_EDGE;
-    double y0[NY > 0 ? NY : 1], v[NQ], hv[NQ];
-    if (recompute_y0) {
-      for (int i = 0; i < NY; ++i) y0[i] = -res[LAM_EDGE(e) + i];
-      lu_solve(we, y0);
-      for (int i = 0; i < NY; ++i) we[WS_Y0 + i] = y0[i];
-    } else {
-      for (int i = 0; i < NY; ++i) y0[i] = we[WS_Y0 + i];
+    if (act) {
+      // ---- reduced blocks ---------------------------------------------------------------------------------------------
+      for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) {
+        const int a = idx / NVP, b = idx - a * NVP;
+        double h = T[(NY + a) * TILE_LD + b] + T[(NY + b) * TILE_LD + a], yty = 0.0;
+        if (!ls_mode)
+          for (int t = DMB_HR_START[a]; t < DMB_HR_START[a + 1]; ++t) if (DMB_HR_COL[t] == b) h += eb[EB_HNZ + DMB_HR_IDX[t]];
+        for (int j = 0; j < NY; ++j) {
+          const double yja = T[j * TILE_LD + NY + a];
+          h += yja * T[j * TILE_LD + TILE_M + b];
+          yty += yja * T[j * TILE_LD + NY + b];
+        }
+        er[ER_HH + idx] = h; er[ER_YTY + idx] = yty;
+      }
+      for (int a = c.gl; a < NVP; a += GSZ) {
+        double g = eb[EB_GOBJ + a] + T[(NY + a) * TILE_LD + NVP], yy = 0.0;
+        for (int j = 0; j < NY; ++j) {
+          const double yja = T[j * TILE_LD + NY + a];
+          g += yja * (eb[EB_GY + j] + T[j * TILE_LD + TILE_M + NVP]);
+          yy += yja * T[j * TILE_LD + NY + NVP];
+        }
+        er[ER_GH + a] = g; er[ER_YTY0 + a] = yy;
+      }
+      for (int idx = c.gl; idx < NX * NVP; idx += GSZ) er[ER_AB + idx] = T[DMB_XF_SEL[idx / NVP] * TILE_LD + NY + idx % NVP];
+      for (int i = c.gl; i < NX; i += GSZ)
+        er[ER_B + i] = T[DMB_XF_SEL[i] * TILE_LD + NY + NVP] + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + i]);
     }
-    for (int i = 0; i < NVP; ++i) v[i] = 0.0;
-    for (int i = 0; i < NY; ++i) v[NVP + i] = y0[i];
-    edge_hmul(we, delta, v, hv);
-    const double* gq = we + WS_GQ;
-    for (int a = 0; a < NVP; ++a) {
-      double g = gq[a] + hv[a], yy = 0.0;
-      for (int j = 0; j < NY; ++j) { g += we[WS_Y + j * NVP + a] * (gq[NVP + j] + hv[NVP + j]); yy += we[WS_Y + j * NVP + a] * y0[j]; }
-      we[WS_GHAT + a] = g;
-      we[WS_YTY0 + a] = yy;
+    WARP_SYNC();
+#if NNL > 0
+    if (act) {
+      // condensed inequality slacks: H += sum_i sig_i d_i d_i', g += sum_i d_i r_i, projected with t_i = T' d_i
+      for (int i = 0; i < NNL; ++i) {
+        double* tv = T + (NY + NVP - 1) * TILE_LD + NE;       // scratch row tail (NVP + 1 entries)
+        for (int a = c.gl; a < NE; a += GSZ) {
+          double s = 0.0;
+          for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) {
+            const int cq = DMB_D_COL[t];
+            if (cq >= NVP) s += eb[EB_DNZ + t] * T[(cq - NVP) * TILE_LD + NY + a];
+            else if (cq == a) s += eb[EB_DNZ + t];
+          }
+          tv[a] = s;
+        }
+        WARP_SYNC();
+        const double sig = eb[EB_SIGS + i], rd = eb[EB_RD + i] + sig * tv[NVP];
+        for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) er[ER_HH + idx] += sig * tv[idx / NVP] * tv[idx % NVP];
+        for (int a = c.gl; a < NVP; a += GSZ) er[ER_GH + a] += tv[a] * rd;
+        WARP_SYNC();
+      }
     }
-    for (int i = 0; i < NX; ++i) we[WS_B + i] = y0[DMB_XF_SEL[i]] + res[LAM_EDGE(e) + NY + i];
+    WARP_SYNC();
+#endif
   }
   CTA_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Riccati sweep over the tree.  Executed by warp 0 (lanes over matrix entries); Qs: shared scratch
-// of size NV*NV + NV + NXI*NV.  Returns 0 on success, 1 if a control block is not positive definite.
-// v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
+// Riccati sweep over the tree, warp 0 (lanes over matrix entries); everything it touches is in shared
+// memory.  Qs: NV*NV + NV + NXI*NV.  v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
+// *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
+DMB_DEV double ab_aug(const double* er, int r, int vi) {      // [A B] of the child state xi_c = (x_c, u_prev_c)
+  if (r < NX) {
+    if (vi < NX) return er[ER_AB + r * NVP + vi];
+    if (vi >= NXI) return er[ER_AB + r * NVP + (vi - NU)];
+    return 0.0;
+  }
+  return vi == NXI + (r - NX) ? 1.0 : 0.0;
+}
+
+DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
   double* Q = Qs;                 // NV x NV
   double* qv = Qs + NV * NV;      // NV
-  double* AB = qv + NV;           // NXI x NV  ([A B] of the current child edge)
-  double* PA = AB + NXI * NV;     // NXI x NV  (P_child [A B])
+  double* PA = qv + NV;           // NXI x NV  (P_child [A B])
   if (c.tid == 0) *flag = 0;
   CTA_SYNC();
   if (c.warp == 0) {
@@ -608,32 +559,29 @@ DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kapp
       double* wn = I.node + (size_t)n * WN_NODE;
       const int k = DMB_NODE_K[n];
       const double* wx = I.w + NODE_OFF(n);
-      const double* lb = I.lb + NODE_OFF(n);
-      const double* ub = I.ub + NODE_OFF(n);
-      const double* zl = I.zL + NODE_OFF(n);
-      const double* zu = I.zU + NODE_OFF(n);
       for (int i = c.lane; i < NV * NV + NV; i += DMB_LANES) Q[i] = 0.0;
       WARP_SYNC();
-      // node-level diagonal terms: Sigma + delta and barrier gradient on (x, u, eps); objective node terms
+      // node-level terms: Sigma + delta and barrier gradient on (x, u, eps); terminal cost; rterm (one lane)
       for (int i = c.lane; i < NVP; i += DMB_LANES) {
         if (k == NHOR && i >= NX) continue;
         const int vi = i < NX ? i : i + NU;           // position in v-space
+        const int gi = NODE_OFF(n) + i;
+        const double lo = I.lb[gi], hi = I.ub[gi];
+        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
         double sig = delta, gb = 0.0;
-        const bool hl = lb[i] > -DMB_INF, hu = ub[i] < DMB_INF;
         if (ls_mode) {
           sig = 1.0;
-          if (hl) gb -= zl[i];
-          if (hu) gb += zu[i];
+          if (hl) gb -= I.zL[gi];
+          if (hu) gb += I.zU[gi];
         } else {
-          if (hl) { const double sl = wx[i] - lb[i]; sig += zl[i] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
-          if (hu) { const double su = ub[i] - wx[i]; sig += zu[i] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
+          if (hl) { const double sl = wx[i] - lo; sig += I.zL[gi] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
+          if (hu) { const double su = hi - wx[i]; sig += I.zU[gi] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
         }
-        Q[vi * NV + vi] += sig;
-        qv[vi] += gb;
+        Q[vi * NV + vi] = sig;
+        qv[vi] = gb;
       }
       WARP_SYNC();
       if (k == NHOR) {
-        // terminal node: mterm
         if (c.lane == 0) {
           const int pe = DMB_NODE_PARENT_EDGE[n];
           double gm[NX], hm[NX * NX];
@@ -646,16 +594,12 @@ DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kapp
           }
         }
         WARP_SYNC();
-        for (int idx = c.lane; idx < NXI * NXI; idx += DMB_LANES) {
-          const int a = idx / NXI, b = idx - a * NXI;
-          wn[WN_P + idx] = Q[a * NV + b];
-        }
+        for (int idx = c.lane; idx < NXI * NXI; idx += DMB_LANES) wn[WN_P + idx] = Q[(idx / NXI) * NV + idx % NXI];
         for (int a = c.lane; a < NXI; a += DMB_LANES) wn[WN_PV + a] = qv[a];
         WARP_SYNC();
         continue;
       }
-      // rterm at this node (weights: reference _mpc.py:1263-1275)
-      if (c.lane == 0) {
+      if (c.lane == DMB_LANES - 1) {
         double up[NU], gr[2 * NU], hr[4 * NU * NU];
         for (int a = 0; a < NU; ++a) up[a] = node_uprev(I, I.w, n, a);
         const double* tv = I.p + DMB_P_TVP + k * DMB_NTVP;
@@ -676,50 +620,42 @@ DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kapp
       WARP_SYNC();
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
-        const double* we = I.edge + (size_t)e * WS_EDGE;
+        const double* er = I.er + (size_t)e * ER_SZ;
         const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
-        // [A B]: child xi = (x_c, u_prev_c) = (Y[xf rows] dvp + b, du)
         for (int idx = c.lane; idx < NXI * NV; idx += DMB_LANES) {
           const int r = idx / NV, vi = idx - r * NV;
           double a = 0.0;
-          if (r < NX) {
-            if (vi < NX) a = we[WS_Y + DMB_XF_SEL[r] * NVP + vi];
-            else if (vi >= NXI) a = we[WS_Y + DMB_XF_SEL[r] * NVP + (vi - NU)];
-          } else if (vi == NXI + (r - NX)) a = 1.0;
-          AB[idx] = a;
-        }
-        WARP_SYNC();
-        for (int idx = c.lane; idx < NXI * NV; idx += DMB_LANES) {
-          const int r = idx / NV, vi = idx - r * NV;
-          double a = 0.0;
-          for (int t = 0; t < NXI; ++t) a += wc[WN_P + r * NXI + t] * AB[t * NV + vi];
+#pragma unroll
+          for (int t = 0; t < NXI; ++t) a += wc[WN_P + r * NXI + t] * ab_aug(er, t, vi);
           PA[idx] = a;
         }
         WARP_SYNC();
-        // Q += embed(Hhat + delta*YtY) + AB' PA ; q += embed(ghat + delta*Yty0) + AB'(P b + p)
-        for (int idx = c.lane; idx < NV * NV; idx += DMB_LANES) {
-          const int a = idx / NV, b = idx - a * NV;
-          double s = 0.0;
-          for (int t = 0; t < NXI; ++t) s += AB[t * NV + a] * PA[t * NV + b];
-          const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < NX ? b : (b >= NXI ? b - NU : -1);
-          if (ia >= 0 && ib >= 0) s += we[WS_HHAT + ia * NVP + ib] + delta * we[WS_YTY + ia * NVP + ib];
-          Q[idx] += s;
-        }
-        for (int a = c.lane; a < NV; a += DMB_LANES) {
-          double s = 0.0;
-          for (int t = 0; t < NXI; ++t) {
-            double pb = wc[WN_PV + t];
-            for (int r = 0; r < NX; ++r) pb += wc[WN_P + t * NXI + r] * we[WS_B + r];
-            s += AB[t * NV + a] * pb;
+        for (int idx = c.lane; idx < NV * NV + NV; idx += DMB_LANES) {
+          if (idx < NV * NV) {
+            const int a = idx / NV, b = idx - a * NV;
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < NXI; ++t) s += ab_aug(er, t, a) * PA[t * NV + b];
+            const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < NX ? b : (b >= NXI ? b - NU : -1);
+            if (ia >= 0 && ib >= 0) s += er[ER_HH + ia * NVP + ib] + delta * er[ER_YTY + ia * NVP + ib];
+            Q[idx] += s;
+          } else {
+            const int a = idx - NV * NV;
+            double s = 0.0;
+            for (int t = 0; t < NXI; ++t) {
+              double pb = wc[WN_PV + t];
+              for (int r = 0; r < NX; ++r) pb += wc[WN_P + t * NXI + r] * er[ER_B + r];
+              s += ab_aug(er, t, a) * pb;
+            }
+            const int ia = a < NX ? a : (a >= NXI ? a - NU : -1);
+            if (ia >= 0) s += er[ER_GH + ia] + delta * er[ER_YTY0 + ia];
+            qv[a] += s;
           }
-          const int ia = a < NX ? a : (a >= NXI ? a - NU : -1);
-          if (ia >= 0) s += we[WS_GHAT + ia] + delta * we[WS_YTY0 + ia];
-          qv[a] += s;
         }
         WARP_SYNC();
       }
-      // eliminate the controls: Cholesky of Q_uu (NUT x NUT), serial (tiny)
-      if (c.lane == 0) {
+      // eliminate the controls: every lane owns one column of [Q_ux | q_u] and solves with its own Cholesky of Q_uu
+      {
         double L[NUT * NUT];
         int bad = 0;
         for (int a = 0; a < NUT; ++a)
@@ -729,9 +665,8 @@ DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kapp
             if (a == b) { if (!(s > 0.0)) { bad = 1; s = 1.0; } L[a * NUT + a] = sqrt(s); }
             else L[a * NUT + b] = s / L[b * NUT + b];
           }
-        if (bad) *flag = 1;
-        // K = -Quu^{-1} Qux ; k = -Quu^{-1} qu
-        for (int col = 0; col <= NXI; ++col) {
+        if (bad && c.lane == 0) *flag = 1;
+        for (int col = c.lane; col <= NXI; col += DMB_LANES) {
           double rhs[NUT];
           for (int a = 0; a < NUT; ++a) rhs[a] = col < NXI ? -Q[(NXI + a) * NV + col] : -qv[NXI + a];
           for (int a = 0; a < NUT; ++a) { double s = rhs[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * rhs[t]; rhs[a] = s / L[a * NUT + a]; }
@@ -740,26 +675,30 @@ DMB_DEV int riccati_backward(const Ctx& c, const Inst& I, double mu, double kapp
         }
       }
       WARP_SYNC();
-      for (int idx = c.lane; idx < NXI * NXI; idx += DMB_LANES) {
-        const int a = idx / NXI, b = idx - a * NXI;
-        double s = Q[a * NV + b];
-        for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_K + t * NXI + b];
-        wn[WN_P + idx] = s;
-      }
-      for (int a = c.lane; a < NXI; a += DMB_LANES) {
-        double s = qv[a];
-        for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_KV + t];
-        wn[WN_PV + a] = s;
+      for (int idx = c.lane; idx < NXI * NXI + NXI; idx += DMB_LANES) {
+        if (idx < NXI * NXI) {
+          const int a = idx / NXI, b = idx - a * NXI;
+          double s = Q[a * NV + b];
+          for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_K + t * NXI + b];
+          wn[WN_P + idx] = s;
+        } else {
+          const int a = idx - NXI * NXI;
+          double s = qv[a];
+          for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_KV + t];
+          wn[WN_PV + a] = s;
+        }
       }
       WARP_SYNC();
     }
   }
   CTA_SYNC();
-  return *flag;
 }
 
-// forward roll-out: dw (all primal steps), new multipliers lamn, inequality steps ds / new y_d
-DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta) {
+// ---------------------------------------------------------------------------------------------------
+// forward roll-out (warp 0) then, per edge by its lane group: dy = Yext [dv; 1], new multipliers by a
+// transposed LU solve in the group tile, inequality steps.
+// ---------------------------------------------------------------------------------------------------
+DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, double* tile_base) {
   if (c.warp == 0) {
     for (int n = 0; n < NNODE; ++n) {
       double* wn = I.node + (size_t)n * WN_NODE;
@@ -773,74 +712,113 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
       if (k == NHOR) { for (int a = NX + c.lane; a < NVP; a += DMB_LANES) dwn[a] = 0.0; WARP_SYNC(); continue; }
       for (int a = c.lane; a < NUT; a += DMB_LANES) {
         double s = wn[WN_KV + a];
+#pragma unroll
         for (int t = 0; t < NXI; ++t) s += wn[WN_K + a * NXI + t] * wn[WN_DXI + t];
         dwn[NX + a] = s;
       }
       WARP_SYNC();
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+      for (int idx = c.lane; idx < DMB_NODE_NEDGE[n] * NXI; idx += DMB_LANES) {
+        const int j = idx / NXI, r = idx - j * NXI;
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
-        const double* we = I.edge + (size_t)e * WS_EDGE;
+        const double* er = I.er + (size_t)e * ER_SZ;
         double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
-        for (int r = c.lane; r < NXI; r += DMB_LANES) {
-          double s;
-          if (r < NX) {
-            s = we[WS_B + r];
-            for (int t = 0; t < NVP; ++t) s += we[WS_Y + DMB_XF_SEL[r] * NVP + t] * dwn[t];
-          } else s = dwn[NX + (r - NX)];
-          wc[WN_DXI + r] = s;
-        }
+        double s;
+        if (r < NX) {
+          s = er[ER_B + r];
+#pragma unroll
+          for (int t = 0; t < NVP; ++t) s += er[ER_AB + r * NVP + t] * dwn[t];
+        } else s = dwn[NX + (r - NX)];
+        wc[WN_DXI + r] = s;
       }
       WARP_SYNC();
     }
-  }
-  CTA_SYNC();
-  // edge unknowns, multipliers
-  for (int e = c.tid; e < NEDGE; e += c.nthr) {
-    const double* we = I.edge + (size_t)e * WS_EDGE;
-    const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
-    double v[NQ], hv[NQ], r[NY > 0 ? NY : 1];
-    for (int i = 0; i < NVP; ++i) v[i] = dvp[i];
-    for (int i = 0; i < NY; ++i) {
-      double s = we[WS_Y0 + i];
-      for (int t = 0; t < NVP; ++t) s += we[WS_Y + i * NVP + t] * dvp[t];
-      v[NVP + i] = s;
-      I.dw[EDGE_OFF(e) + i] = s;
-    }
-    // continuity multiplier = gradient of the child's cost-to-go
-    const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
-    double lc[NX];
-    for (int a = 0; a < NX; ++a) {
-      double s = wc[WN_PV + a];
-      for (int t = 0; t < NXI; ++t) s += wc[WN_P + a * NXI + t] * wc[WN_DXI + t];
-      lc[a] = s;
-      I.lamn[LAM_EDGE(e) + NY + a] = s;
-    }
-    edge_hmul(we, delta, v, hv);
-    for (int i = 0; i < NY; ++i) r[i] = -(we[WS_GQ + NVP + i] + hv[NVP + i]);
-    for (int a = 0; a < NX; ++a) r[DMB_XF_SEL[a]] -= lc[a];
-    lu_solve_t(we, r);
-    for (int i = 0; i < NY; ++i) I.lamn[LAM_EDGE(e) + i] = r[i];
-#if NNL > 0
-    {
-      double jd[NNL];
-      for (int i = 0; i < NNL; ++i) jd[i] = 0.0;
-      for (int kk = 0; kk < DMB_NNZ_D; ++kk) jd[DMB_D_ROW[kk]] += we[WS_DNZ + kk] * v[DMB_D_COL[kk]];
-      for (int i = 0; i < NNL; ++i) {
-        const double dsi = jd[i] + res[LAM_EDGE(e) + NY + NX + i];
-        I.ds[e * NNL + i] = dsi;
-        // y_d+ = Sigma_s ds + grad_s phi = Sigma_s*J dq + r_d
-        I.lamn[LAM_EDGE(e) + NY + NX + i] = we[WS_SIGS + i] * jd[i] + we[WS_RD + i];
-      }
-    }
-#endif
-  }
-  {
     const double* w0 = I.node;
-    for (int a = c.tid; a < NX; a += c.nthr) {
+    for (int a = c.lane; a < NX; a += DMB_LANES) {
       double s = w0[WN_PV + a];
       for (int t = 0; t < NXI; ++t) s += w0[WN_P + a * NXI + t] * w0[WN_DXI + t];
       I.lamn[a] = -s;
     }
+  }
+  CTA_SYNC();
+  double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  double* dq = T + NY * TILE_LD;            // scratch behind the LU copy: dq (NQ), then r (NY)
+  double* rv = dq + NQ;
+  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
+    const int e = e0 + c.grp;
+    const bool act = e < NEDGE;
+    const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+    if (act) {
+      const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
+      for (int idx = c.gl; idx < NY * NY; idx += GSZ) T[(idx / NY) * TILE_LD + idx % NY] = eb[EB_LU + idx];
+      for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];
+      for (int i = c.gl; i < NY; i += GSZ) {
+        double s = eb[EB_Y + i * NE + NVP];
+#pragma unroll
+        for (int t = 0; t < NVP; ++t) s += eb[EB_Y + i * NE + t] * dvp[t];
+        dq[NVP + i] = s;
+        I.dw[EDGE_OFF(e) + i] = s;
+      }
+      // continuity multiplier = gradient of the child's cost-to-go
+      const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+      for (int a = c.gl; a < NX; a += GSZ) {
+        double s = wc[WN_PV + a];
+#pragma unroll
+        for (int t = 0; t < NXI; ++t) s += wc[WN_P + a * NXI + t] * wc[WN_DXI + t];
+        I.lamn[LAM_EDGE(e) + NY + a] = s;
+      }
+    }
+    WARP_SYNC();
+#if NNL > 0
+    double* jd = rv + NY;                    // NNL entries
+    if (act) {
+      for (int i = c.gl; i < NNL; i += GSZ) {
+        double s = 0.0;
+        for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) s += eb[EB_DNZ + t] * dq[DMB_D_COL[t]];
+        jd[i] = s;
+        I.ds[e * NNL + i] = s + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + NX + i]);
+        // y_d+ = Sigma_s ds + grad_s phi = Sigma_s J dq + r_d
+        I.lamn[LAM_EDGE(e) + NY + NX + i] = eb[EB_SIGS + i] * s + eb[EB_RD + i];
+      }
+    }
+    WARP_SYNC();
+#endif
+    if (act) {
+      // r_y = -(g_y + [H_e dq]_y) - E' lam_C
+      for (int j = c.gl; j < NY; j += GSZ) {
+        double s = eb[EB_GY + j] + (eb[EB_SIGY + j] + delta) * dq[NVP + j];
+        if (!ls_mode)
+          for (int t = DMB_HR_START[NVP + j]; t < DMB_HR_START[NVP + j + 1]; ++t) s += eb[EB_HNZ + DMB_HR_IDX[t]] * dq[DMB_HR_COL[t]];
+#if NNL > 0
+        for (int t = 0; t < DMB_NNZ_D; ++t) if (DMB_D_COL[t] == NVP + j) s += eb[EB_DNZ + t] * (eb[EB_SIGS + DMB_D_ROW[t]] * jd[DMB_D_ROW[t]] + eb[EB_RD + DMB_D_ROW[t]]);
+#endif
+        rv[j] = -s;
+      }
+    }
+    WARP_SYNC();
+    if (act) {
+      for (int a = c.gl; a < NX; a += GSZ) rv[DMB_XF_SEL[a]] -= I.lamn[LAM_EDGE(e) + NY + a];
+    }
+    WARP_SYNC();
+    // ---- G_y' lam = r with P G_y = L U:  U' a = r ; L' b = a ; lam = P' b.  Column sweeps, lanes over rows ---------
+    for (int k = 0; k < NY; ++k) {
+      if (act && c.gl == 0) rv[k] /= T[k * TILE_LD + k];
+      WARP_SYNC();
+      if (act) { const double ak = rv[k]; for (int r = k + 1 + c.gl; r < NY; r += GSZ) rv[r] -= T[k * TILE_LD + r] * ak; }
+      WARP_SYNC();
+    }
+    for (int k = NY - 1; k >= 0; --k) {
+      if (act) { const double bk = rv[k]; for (int r = c.gl; r < k; r += GSZ) rv[r] -= T[k * TILE_LD + r] * bk; }
+      WARP_SYNC();
+    }
+    if (act && c.gl == 0) {
+      for (int k = NY - 1; k >= 0; --k) {
+        const int pr = (int)eb[EB_PIV + k];
+        if (pr != k) { const double t = rv[k]; rv[k] = rv[pr]; rv[pr] = t; }
+      }
+    }
+    WARP_SYNC();
+    if (act) for (int j = c.gl; j < NY; j += GSZ) I.lamn[LAM_EDGE(e) + j] = rv[j];
+    WARP_SYNC();
   }
   CTA_SYNC();
 }

@@ -68,15 +68,8 @@ DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, dou
   *s_c = fmax(s_max, SZ / fmax(NZ, 1.0)) / s_max;
 }
 
-// full structured solve: edges already factorised for the current point
-DMB_DEV void direction(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, double delta, int ls_mode,
-                       int recompute_y0, double* Qs, DmbShared* S) {
-  solve_edges(c, I, res, delta, recompute_y0);
-  riccati_backward(c, I, mu, kappa_d, delta, ls_mode, Qs, &S->flag);
-}
-
 DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o, const double* x0_internal,
-                            double* tile, double* hq, double* Qs, DmbShared* S, DmbResult* out) {
+                            double* tile, double* Qs, DmbShared* S, DmbResult* out) {
   Inst I = I_in;
   double* red = S->red;
   // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
@@ -84,10 +77,10 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   for (int i = c.tid; i < NLAM; i += c.nthr) { I.dc[i] = 1.0; I.lam[i] = 0.0; }
   I.df = 1.0;
   CTA_SYNC();
-  eval_gradient(c, I, I.w, I.lam, 0, I.gl);
+  eval_derivatives(c, I);
   {
     double g = 0.0;
-    for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.gl[i]));
+    for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.go[i]));
     g = block_max(c, g, red);
     if (g > o.nlp_scaling_max_gradient) I.df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
   }
@@ -141,13 +134,12 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
 #endif
   // ---- least-squares multiplier estimate ----------------------------------------------------------------------------
   if (c.tid == 0) { S->fail = 0; S->n_filt = 0; }
-  CTA_SYNC();
-  factor_edges(c, I, 0.0, 0.0, 1, tile, hq, &S->fail);
-  CTA_SYNC();
   for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = 0.0;
   CTA_SYNC();
-  direction(c, I, I.rest, 0.0, 0.0, 0.0, 1, 1, Qs, S);
-  forward_recover(c, I, I.rest, 0.0);
+  eval_derivatives(c, I);                       // lam = 0: objective gradient and Jacobian at the pushed point
+  factor_edges(c, I, I.rest, 0.0, 0.0, 1, tile, &S->fail);
+  riccati_backward(c, I, 0.0, 0.0, 0.0, 1, Qs, &S->flag);
+  forward_recover(c, I, I.rest, 0.0, 1, tile);
   {
     double m = 0.0;
     for (int i = c.tid; i < NLAM; i += c.nthr) m = fmax(m, fabs(I.lamn[i]));
@@ -166,7 +158,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
 
   while (true) {
     // ---- convergence tests ----------------------------------------------------------------------------------------------
-    eval_gradient(c, I, I.w, I.lam, 1, I.gl);
+    eval_derivatives(c, I);
     double dual, cmpl, s_d, s_c;
     kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
     dual0 = dual;
@@ -201,13 +193,12 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     // ---- search direction ------------------------------------------------------------------------------------------------
     if (c.tid == 0) S->fail = 0;
     CTA_SYNC();
-    factor_edges(c, I, mu, o.kappa_d, 0, tile, hq, &S->fail);
-    CTA_SYNC();
+    factor_edges(c, I, I.res, mu, o.kappa_d, 0, tile, &S->fail);
     double delta_w = 0.0;
     if (degenerate_reg) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
     bool step_fail = S->fail != 0;
     while (!step_fail) {
-      direction(c, I, I.res, mu, o.kappa_d, delta_w, 0, 0, Qs, S);
+      riccati_backward(c, I, mu, o.kappa_d, delta_w, 0, Qs, &S->flag);
       if (!S->flag) break;
       if (delta_w == 0.0) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
       else delta_w *= (delta_w_last == 0.0 ? o.kappa_w_plus_first : o.kappa_w_plus);
@@ -215,14 +206,13 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     }
     if (step_fail) { status = DMB_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
-    forward_recover(c, I, I.res, delta_w);
+    forward_recover(c, I, I.res, delta_w, 0, tile);
 
-    // ---- step sizes, directional derivative ----------------------------------------------------------------------------
-    eval_gradient(c, I, I.w, I.lam, 0, I.gl);            // objective gradient (scaled by df)
+    // ---- step sizes, directional derivative (I.go = objective gradient, scaled by df) ------------------------------
     double a_max = 1.0, a_z = 1.0, dphi = 0.0;
     for (int i = c.tid; i < NWI; i += c.nthr) {
       const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
-      double g = I.gl[i];
+      double g = I.go[i];
       const double d = I.dw[i];
       if (hl) {
         const double sl = I.w[i] - I.lb[i];
@@ -405,10 +395,3 @@ DMB_DEV void store_solution(const Ctx& c, const Inst& I, double df, double* x_ou
   CTA_SYNC();
 }
 
-DMB_DEV void bind_instance(Inst& I, double* vec, double* ws_edge_node) {
-  I.w = vec + WV_W; I.wt = vec + WV_WT; I.dw = vec + WV_DW; I.zL = vec + WV_ZL; I.zU = vec + WV_ZU;
-  I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
-  I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU; I.gl = vec + WV_GL;
-  I.edge = ws_edge_node; I.node = ws_edge_node + (size_t)NEDGE * WS_EDGE;
-}
-#define DMB_QS_SIZE (NV * NV + NV + 2 * NXI * NV)

@@ -32,29 +32,45 @@ def _kernel_sources_digest() -> str:
     return h.hexdigest()
 
 
-def launch_config(r: Recipe):
-    """Threads per CTA and whether the iterate vectors fit in shared memory (227 KB per CTA on sm_100)."""
+def smem_doubles(r: Recipe, threads: int):
+    """Mirror of the shared-memory carve-up in csrc/dmb_api.cu / ipm_core.cuh (doubles): (fixed part, iterate vectors)."""
     n_vp = r.n_x + r.n_u + r.n_eps
-    n_q = n_vp + r.n_y
+    n_e = n_vp + 1
     n_node, n_edge = len(r.node_k), len(r.edge_k)
+    nnl = r.nl_rows_per_edge
     nwi = n_node * n_vp + n_edge * r.n_y
-    nlam = r.n_x + n_edge * (r.n_y + r.n_x + r.nl_rows_per_edge)
-    wv = 6 * nwi + 5 * nlam + 4 * n_edge * r.nl_rows_per_edge
+    nlam = r.n_x + n_edge * (r.n_y + r.n_x + nnl)
+    gsz = 16 if r.n_y <= 16 else 32
+    tile = (threads // gsz) * (r.n_y + n_vp) * ((r.n_y + 2 * n_e) | 1)
+    nxi, nut = r.n_x + r.n_u, r.n_u + r.n_eps
+    nv = nxi + nut
+    qs = nv * nv + nv + nxi * nv + 8
+    er = n_edge * (r.n_x * n_vp + r.n_x + 2 * n_vp * n_vp + 2 * n_vp)
+    node = n_node * (nxi * nxi + nxi + nut * nxi + nut + nxi)
+    vec = 7 * nwi + 5 * nlam + 4 * n_edge * nnl
+    return tile + qs + er + node + 64, vec
+
+
+def launch_config(r: Recipe):
+    """Threads per CTA, whether the iterate vectors live in shared memory, and the CTAs/SM the register budget is
+    compiled for (227 KB of shared memory per SM on sm_100)."""
     threads = 128
-    tile = (threads // 32) * (r.n_y * ((r.n_y + 2 * n_vp + 1) | 1) + n_q * (n_q | 1))
-    nxi, nv = r.n_x + r.n_u, r.n_x + 2 * r.n_u + r.n_eps
-    qs = nv * nv + nv + 2 * nxi * nv
-    fixed = 8 * (tile + qs) + 2048
-    vec_smem = int(fixed + 8 * wv <= 100 * 1024)       # keep >= 2 CTAs per SM
-    if fixed > 200 * 1024:
+    fixed, vec = smem_doubles(r, threads)
+    if 8 * fixed > 200 * 1024:
         threads = 64
-    return threads, vec_smem
+        fixed, vec = smem_doubles(r, threads)
+    if 8 * fixed > 220 * 1024:
+        raise NotImplementedError(f"problem too large for the shared-memory resident solver ({8 * fixed} bytes per CTA)")
+    vec_smem = int(8 * (fixed + vec) <= 113 * 1024)
+    total = 8 * (fixed + (vec if vec_smem else 0)) + 1024
+    min_ctas = max(1, min(4, (227 * 1024) // total))
+    return threads, vec_smem, min_ctas
 
 
 def build_library(r: Recipe, verbose: bool = False) -> Path:
     src = generate(r)
-    threads, vec_smem = launch_config(r)
-    key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{vec_smem}").encode()).hexdigest()[:16]
+    threads, vec_smem, min_ctas = launch_config(r)
+    key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{vec_smem}{min_ctas}").encode()).hexdigest()[:16]
     d = CACHE / key
     lib = d / f"libdmb_{key}.so"
     if lib.exists():
@@ -62,7 +78,7 @@ def build_library(r: Recipe, verbose: bool = False) -> Path:
     d.mkdir(parents=True, exist_ok=True)
     (d / "problem_gen.h").write_text(src)
     cmd = [NVCC, *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-           f"-DDMB_THREADS={threads}", f"-DDMB_VEC_SMEM={vec_smem}", f"-I{d}", f"-I{CSRC}", f"-I{INCLUDE}",
+           f"-DDMB_THREADS={threads}", f"-DDMB_VEC_SMEM={vec_smem}", f"-DDMB_MIN_CTAS={min_ctas}", f"-I{d}", f"-I{CSRC}", f"-I{INCLUDE}",
            str(CSRC / "dmb_api.cu"), "-o", str(lib) + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

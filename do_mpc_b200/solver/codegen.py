@@ -102,6 +102,34 @@ def generate(r: Recipe) -> str:
                    "  (void)lam; (void)lnl; (void)sig_l; (void)sig_e;\n" +
                    (E.emit_c([(f"hnz[{k}]", e) for k, e in enumerate(hn)], inpL) if hn else "  (void)hnz;")))
 
+    # ---- fused derivative evaluation at one point (shares all common sub-expressions) ----------------------------------
+    # objective-only gradient: L with lam = lnl = 0
+    Lobj = E.mk(E.ADD, E.mk(E.MUL, sig_l, lt), E.mk(E.MUL, sig_e, ec))
+    gO = E.gradient(Lobj, q_ids)
+    gC = [E.mk(E.SUB, a, b) for a, b in zip(gL, gO)]
+    fused = ([(f"gobj[{i}]", e) for i, e in enumerate(gO)] + [(f"gcon[{i}]", e) for i, e in enumerate(gC)] +
+             [(f"jnz[{k}]", e) for k, e in enumerate(jn)] + [(f"hnz[{k}]", e) for k, e in enumerate(hn)] +
+             [(f"dnz[{k}]", e) for k, e in enumerate(dn)])
+    out.append(_fn("gen_derivs", lag_args + ", double* __restrict__ gobj, double* __restrict__ gcon, double* __restrict__ jnz, "
+                   "double* __restrict__ hnz, double* __restrict__ dnz",
+                   "  (void)lam; (void)lnl; (void)hnz; (void)dnz;\n" + E.emit_c(fused, inpL)))
+    # row-wise (CSR) views: J rows (nonzeros are emitted row-major), full symmetric H rows
+    jr_start = [0] * (len(G_ids) + 1)
+    for r_ in jr: jr_start[r_ + 1] += 1
+    for i in range(len(G_ids)): jr_start[i + 1] += jr_start[i]
+    hrows = [[] for _ in range(n_q)]
+    for k, (r_, c_) in enumerate(zip(hr, hc)):
+        hrows[r_].append((c_, k))
+        if r_ != c_: hrows[c_].append((r_, k))
+    hr_start, hr_col, hr_idx = [0], [], []
+    for row in hrows:
+        for c_, k in sorted(row):
+            hr_col.append(c_); hr_idx.append(k)
+        hr_start.append(len(hr_col))
+    dr_start = [0] * (n_nl + 1)
+    for r_ in dr: dr_start[r_ + 1] += 1
+    for i in range(n_nl): dr_start[i + 1] += dr_start[i]
+
     # ---- rterm (u, u_prev, tvp) ------------------------------------------------------------------------------------------
     inpR = {}
     for i, s in enumerate(u_ids): inpR[s] = f"u[{i}]"
@@ -180,6 +208,10 @@ def generate(r: Recipe) -> str:
     H.append(_ctab("int", "DMB_J_ROW", jr)); H.append(_ctab("int", "DMB_J_COL", jc))
     H.append(_ctab("int", "DMB_H_ROW", hr)); H.append(_ctab("int", "DMB_H_COL", hc))
     H.append(_ctab("int", "DMB_D_ROW", dr)); H.append(_ctab("int", "DMB_D_COL", dcol))
+    H.append(_ctab("int", "DMB_JR_START", jr_start)); H.append(_ctab("int", "DMB_DR_START", dr_start))
+    H.append(_ctab("int", "DMB_HR_START", hr_start)); H.append(_ctab("int", "DMB_HR_COL", hr_col))
+    H.append(_ctab("int", "DMB_HR_IDX", hr_idx))
+    H.append(f"#define DMB_NNZ_HR {max(len(hr_col), 1)}")
     # internal <-> flat (reference order) maps
     n_edge = len(r.edge_k)
     w2f = []

@@ -18,20 +18,22 @@ void hostsim_default_options(DmbOptions* o) { dmb_fill_default_options(o); }
 int hostsim_solve(int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s, const double* p,
                   const double* lbx, const double* ubx, const DmbOptions* opts,
                   double* x, double* lam_g, double* lam_x, double* g, double* f, int* status, int* iters, double* u0) {
-  std::vector<double> lbI(NWI), ubI(NWI), vec(WV_END), ws((size_t)NEDGE * WS_EDGE + (size_t)NNODE * WN_NODE);
-  std::vector<double> tile((size_t)NY * TILE_LD + 1), hq((size_t)NQ * HQ_LD + 1), Qs(DMB_QS_SIZE), x0i(NWI);
+  std::vector<double> lbI(NWI), ubI(NWI), vec(WV_END), er((size_t)NEDGE * ER_SZ), node((size_t)NNODE * WN_NODE),
+      eb((size_t)NEDGE * EB_SZ);
+  std::vector<double> tile((size_t)TILE_SZ + 1), Qs(DMB_QS_SIZE), x0i(NWI);
   dmb_internal_bounds(lbx, ubx, opts, lbI.data(), ubI.data());
-  Ctx c{0, 1, 0, 0, 1};
+  Ctx c{0, 1, 0, 0, 1, 0, 0, 1};
   DmbShared S;
   for (int b = 0; b < B; ++b) {
     Inst I;
-    bind_instance(I, vec.data(), ws.data());
+    bind_vectors(I, vec.data());
+    I.er = er.data(); I.node = node.data(); I.eb = eb.data();
     I.p = p + (size_t)b * DMB_NP; I.lb = lbI.data(); I.ub = ubI.data(); I.df = 1.0;
     I.relax_fac = opts->bound_relax_factor; I.relax_max = opts->constr_viol_tol;
     load_initial_guess(c, x_init ? x_init + (size_t)b * DMB_NW : nullptr, x0s ? x0s + (size_t)b * DMB_NX : nullptr,
                        u0s ? u0s + (size_t)b * DMB_NU : nullptr, z0s ? z0s + (size_t)b * DMB_NZ : nullptr, x0i.data());
     DmbResult r;
-    solve_instance(c, I, *opts, x0i.data(), tile.data(), hq.data(), Qs.data(), &S, &r);
+    solve_instance(c, I, *opts, x0i.data(), tile.data(), Qs.data(), &S, &r);
     I.df = r.df;
     if (x && x_init) for (int i = 0; i < DMB_NW; ++i) x[(size_t)b * DMB_NW + i] = x_init[(size_t)b * DMB_NW + i];
     store_solution(c, I, r.df, x ? x + (size_t)b * DMB_NW : nullptr, lam_g ? lam_g + (size_t)b * DMB_NG : nullptr,
