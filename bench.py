@@ -269,6 +269,11 @@ def main():
         traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get("dram_bytes_per_launch")
     except Exception:
         pass
+    st_ = out["stats"].cpu().numpy()
+    sub = st_[:, 13:21].sum(axis=0)
+    ph = st_[:, 4:13].sum(axis=0)
+    phases = {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
+        ["derivs", "kkt_mu", "factor", "riccati", "forward_recover", "stepsize", "linesearch", "accept", "init"], ph)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -283,7 +288,9 @@ def main():
                     "d2h_bytes_per_step": int(B * (r.n_u * 8 + 8 + 4 + 4 + 4 * 8))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms, "phase_share_of_cta_cycles": phases,
+                         "subphase_share": {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
+                             ["f_assemble", "f_lu", "f_backsub", "f_mn", "f_reduce", "ric_sweep", "fwd_sweep", "-"], sub)},
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "algorithmic bytes = A_B(23.3 KB)/IPM iteration x total iterations; iterate state lives in shared memory, "
                                  "so DRAM traffic is far below this and the kernel is latency/issue bound (DESIGN.md §Roofline)"},

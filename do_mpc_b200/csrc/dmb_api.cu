@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
   Inst I;
   bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot);
   I.er = sm + SM_ER; I.node = sm + SM_NODE; I.eb = slot + (DMB_VEC_SMEM ? 0 : WV_END);
-  I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0;
+  I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
   while (true) {
     if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_INF_PR] = result.inf_pr;
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_INF_DU] = result.inf_du;
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_OBJ_SCALE] = result.df;
+        for (int i = 0; i < DMB_NPHASE; ++i) a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_PHASE0 + i] = (double)result.phase_cycles[i];
       }
     }
     __syncthreads();

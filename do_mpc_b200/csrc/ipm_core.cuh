@@ -30,6 +30,7 @@ struct Ctx { int tid, nthr, lane, warp, nwarp, gl, grp, ngrp; };
 
 #ifdef DMB_HOSTSIM
 #define DMB_DEV
+static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #define DMB_LANES 1
 #define CTA_SYNC() ((void)0)
 #define WARP_SYNC() ((void)0)
@@ -96,12 +97,22 @@ enum DmbStatus {
 #else
 #define GSZ (NY <= 16 ? 16 : 32)
 #endif
-// LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], then NVP rows of N = H_vy*Yext
+// LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], then NVP rows of N = H_vy*Yext, then a
+// staging area for the bulk per-edge data (global loads never sit inside dependent inner loops)
 #define TILE_NC (NY + NE)
 #define TILE_M (NY + NE)
 #define TILE_LD ((NY + 2 * NE) | 1)                   // odd leading dimension: conflict-free 64-bit rows
 #define TILE_ROWS (NY + NVP)
-#define TILE_SZ (TILE_ROWS * TILE_LD)
+#define STG_HNZ (TILE_ROWS * TILE_LD)
+#define STG_GOBJ (STG_HNZ + DMB_NNZ_H)
+#define STG_GY (STG_GOBJ + NQ)
+#define STG_SIGY (STG_GY + NY)
+#define STG_DNZ (STG_SIGY + NY)
+#define STG_SIGS (STG_DNZ + DMB_NNZ_D)
+#define STG_RD (STG_SIGS + NNL)
+#define STG_DQ (STG_RD + NNL)                          // recovery: dq (NQ), r (NY), jd (NNL)
+#define STG_INVD (STG_DQ + NQ + NY + NNL)              // reciprocal pivots (NY)
+#define TILE_SZ (STG_INVD + NY)
 
 // per-edge reduced data kept in shared memory (inputs of the Riccati sweep)
 #define ER_AB 0                                        // Y[xf rows] : NX x NVP
@@ -125,13 +136,18 @@ enum DmbStatus {
 #define EB_SIGS (EB_SIGY + NY)
 #define EB_RD (EB_SIGS + NNL)
 #define EB_SZ (EB_RD + NNL)
-// per-node data in shared memory
-#define WN_P 0                                          // P (NXI x NXI)
-#define WN_PV (WN_P + NXI * NXI)                        // p (NXI)
-#define WN_K (WN_PV + NXI)                              // K (NUT x NXI)
+// per-node data in shared memory.  Q (NV x NV, v-space) is assembled in parallel (node terms + projected edge
+// Hessians), completed and reduced in place by the sweep: afterwards its leading NXI x NXI block (stride NV) is P.
+#define WN_Q 0                                          // Q / P (NV x NV)
+#define WN_QV (WN_Q + NV * NV)                          // q / p (NV)
+#define WN_K (WN_QV + NV)                               // K (NUT x NXI)
 #define WN_KV (WN_K + NUT * NXI)                        // k (NUT)
 #define WN_DXI (WN_KV + NUT)                            // d xi (NXI)
-#define WN_NODE (WN_DXI + NXI)
+#define WN_RG (WN_DXI + NXI)                            // weighted rterm gradient (u, u_prev)
+#define WN_RH (WN_RG + 2 * NU)                          // weighted rterm Hessian (2NU x 2NU)
+#define WN_NODE (WN_RH + 4 * NU * NU)
+#define P_AT(wn, a, b) (wn)[WN_Q + (a) * NV + (b)]
+#define VPOS(i) ((i) < NX ? (i) : (i) + NU)             // position of edge-local node variable i in v-space
 // iterate vectors
 #define WV_W 0
 #define WV_WT (WV_W + NWI)
@@ -150,9 +166,17 @@ enum DmbStatus {
 #define WV_DS (WV_ST + NEDGE * NNL)
 #define WV_VU (WV_DS + NEDGE * NNL)
 #define WV_END (WV_VU + NEDGE * NNL)
-#define DMB_QS_SIZE (NV * NV + NV + NXI * NV + 8)
+#define DMB_QS_SIZE (NXI * NVP + NXI + 8)
 
+#ifdef DMB_HOSTSIM
+#define DMB_CLOCK() 0LL
+#else
+#define DMB_CLOCK() clock64()
+#endif
+#define DMB_NSUB 8
+#define SUB_TICK(I, ph) do { if ((I).sub) { const long long t_ = DMB_CLOCK(); (I).sub[ph] += t_ - tsub_; tsub_ = t_; } } while (0)
 struct Inst {
+  long long* sub;      // optional fine-grained cycle counters (thread 0 only), see SUB_TICK
   double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *res, *rest, *dc, *s, *st, *ds, *vU;
   double *er, *node, *eb;
   const double *p, *lb, *ub;
@@ -320,6 +344,23 @@ DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
     for (int k = 0; k < DMB_NNZ_D; ++k) eb[EB_DNZ + k] *= dc[NY + NX + DMB_D_ROW[k]];
 #endif
   }
+  // weighted rterm derivatives per node (reference _mpc.py:1263-1275), used by the gradients below and the sweep
+  for (int n = c.nthr - 1 - c.tid; n < NNODE; n += c.nthr) {
+    double* wn = I.node + (size_t)n * WN_NODE;
+    const int k = DMB_NODE_K[n];
+    if (k == NHOR) continue;
+    double up[NU], gr[2 * NU], hr[4 * NU * NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) up[a] = node_uprev(I, w, n, a);
+    const double* tv = I.p + DMB_P_TVP + k * DMB_NTVP;
+    gen_rterm_grad(w + NODE_OFF(n) + NX, up, tv, gr);
+    gen_rterm_hess(w + NODE_OFF(n) + NX, up, tv, hr);
+    const double wgt = I.df * DMB_NODE_RW[n];
+#pragma unroll
+    for (int a = 0; a < 2 * NU; ++a) wn[WN_RG + a] = wgt * gr[a];
+#pragma unroll
+    for (int a = 0; a < 4 * NU * NU; ++a) wn[WN_RH + a] = wgt * hr[a];
+  }
   CTA_SYNC();
   // node variables: sum over child edges (+ continuity of the parent edge, terminal cost, rterm)
   for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
@@ -344,17 +385,12 @@ DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
       } else gc += I.lam[i];
     } else if (i < NX + NU) {
       const int iu = i - NX;
-      double up[NU], gr[2 * NU];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) up[a] = node_uprev(I, w, n, a);
-      gen_rterm_grad(w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + k * DMB_NTVP, gr);
-      go += I.df * DMB_NODE_RW[n] * gr[iu];
+      go += I.node[(size_t)n * WN_NODE + WN_RG + iu];
       // this node's input is u_prev of every child node that still has a control
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int cn = DMB_EDGE_CHILD[DMB_NODE_FIRST_EDGE[n] + j];
         if (DMB_NODE_K[cn] == NHOR) continue;
-        gen_rterm_grad(w + NODE_OFF(cn) + NX, w + NODE_OFF(n) + NX, I.p + DMB_P_TVP + (k + 1) * DMB_NTVP, gr);
-        go += I.df * DMB_NODE_RW[cn] * gr[NU + iu];
+        go += I.node[(size_t)cn * WN_NODE + WN_RG + NU + iu];
       }
     }
     I.go[idx] = go; I.gl[idx] = go + gc;
@@ -378,6 +414,7 @@ DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
 DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
                           double* tile_base, int* fail) {
   double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  long long tsub_ = DMB_CLOCK();
   for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
@@ -385,7 +422,13 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
     double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
     const double* dc = I.dc + LAM_EDGE(act ? e : 0);
     if (act) {
-      for (int i = c.gl; i < TILE_SZ; i += GSZ) T[i] = 0.0;
+      for (int i = c.gl; i < TILE_ROWS * TILE_LD; i += GSZ) T[i] = 0.0;
+      // stage the bulk data of this edge (coalesced, independent loads)
+      for (int i = c.gl; i < DMB_NNZ_H; i += GSZ) T[STG_HNZ + i] = ls_mode ? 0.0 : eb[EB_HNZ + i];
+      for (int i = c.gl; i < NQ; i += GSZ) T[STG_GOBJ + i] = eb[EB_GOBJ + i];
+#if NNL > 0
+      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
+#endif
     }
     WARP_SYNC();
     if (act) {
@@ -406,24 +449,28 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
           if (hl) gb -= I.zL[i];
           if (hu) gb += I.zU[i];
         } else {
-          if (hl) { const double sl = wy - lo; sig += I.zL[i] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
-          if (hu) { const double su = hi - wy; sig += I.zU[i] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
+          if (hl) { const double rs = 1.0 / (wy - lo); sig += I.zL[i] * rs; gb -= mu * rs; if (!hu) gb += kappa_d * mu; }
+          if (hu) { const double rs = 1.0 / (hi - wy); sig += I.zU[i] * rs; gb += mu * rs; if (!hl) gb -= kappa_d * mu; }
         }
+        T[STG_SIGY + r] = sig;
+        T[STG_GY + r] = T[STG_GOBJ + NVP + r] + gb;
         eb[EB_SIGY + r] = sig;
-        eb[EB_GY + r] = eb[EB_GOBJ + NVP + r] + gb;
+        eb[EB_GY + r] = T[STG_GY + r];
       }
 #if NNL > 0
       for (int i = c.gl; i < NNL; i += GSZ) {
         const double sl = nl_ub_relaxed(I, e, i) - I.s[e * NNL + i];
         const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
-        eb[EB_SIGS + i] = sig;
         // r_d = Sigma_s (d - s) + grad_s phi ; grad_s phi = mu/sl - kappa_d*mu (upper bound only)
-        eb[EB_RD + i] = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
+        const double rd = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
+        T[STG_SIGS + i] = sig; T[STG_RD + i] = rd;
+        eb[EB_SIGS + i] = sig; eb[EB_RD + i] = rd;
       }
 #endif
     }
     WARP_SYNC();
-    // ---- LU with partial pivoting; columns [NY, TILE_NC) ride along -------------------------------------------------
+    SUB_TICK(I, 0);
+    // ---- LU with partial pivoting; columns [NY, TILE_NC) ride along.  The diagonal keeps the RECIPROCAL pivot. ------
     for (int k = 0; k < NY; ++k) {
       double best = -1.0; int myr = -1;
       if (act) for (int r = c.gl; r < NY; r += GSZ) if (r >= k) { const double a = fabs(T[r * TILE_LD + k]); if (a > best) { best = a; myr = r; } }
@@ -442,50 +489,56 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
         for (int r = c.gl; r < NY; r += GSZ) if (r > k) {
           const double l = T[r * TILE_LD + k] * inv;
           T[r * TILE_LD + k] = l;
-#pragma unroll 4
+#pragma unroll 6
           for (int cc = k + 1; cc < TILE_NC; ++cc) T[r * TILE_LD + cc] -= l * T[k * TILE_LD + cc];
         }
+        if (c.gl == 0) T[STG_INVD + k] = inv;
       }
       WARP_SYNC();
     }
+    SUB_TICK(I, 1);
     if (act) {
-      for (int idx = c.gl; idx < NY * NY; idx += GSZ) eb[EB_LU + idx] = T[(idx / NY) * TILE_LD + idx % NY];
+      for (int idx = c.gl; idx < NY * NY; idx += GSZ) {
+        const int r = idx / NY, cc = idx - r * NY;
+        eb[EB_LU + idx] = r == cc ? T[STG_INVD + r] : T[r * TILE_LD + cc];
+      }
       // ---- back substitution, one lane per right-hand side; then Yext = [-X | x_rhs] --------------------------------
       for (int j = c.gl; j < NE; j += GSZ) {
         for (int k = NY - 1; k >= 0; --k) {
           double x = T[k * TILE_LD + NY + j];
           for (int cc = k + 1; cc < NY; ++cc) x -= T[k * TILE_LD + cc] * T[cc * TILE_LD + NY + j];
-          T[k * TILE_LD + NY + j] = x / T[k * TILE_LD + k];
+          T[k * TILE_LD + NY + j] = x * T[STG_INVD + k];
         }
         if (j < NVP) for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = -T[k * TILE_LD + NY + j];
       }
     }
     WARP_SYNC();
+    SUB_TICK(I, 2);
     if (act) {
-      for (int idx = c.gl; idx < NY * NE; idx += GSZ) eb[EB_Y + idx] = T[(idx / NE) * TILE_LD + NY + idx % NE];
+      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; eb[EB_Y + idx] = T[r * TILE_LD + NY + idx - r * NE]; }
       // ---- M = (H_yy + Sigma_y) Yext  (rows NY, cols NE) and N = H_vy Yext (rows NVP) via the CSR rows of H ----------
       for (int idx = c.gl; idx < NQ * NE; idx += GSZ) {
         const int rq = idx / NE, a = idx - rq * NE;            // rq < NVP: N row, else M row
         double s = 0.0;
-        if (!ls_mode)
-          for (int t = DMB_HR_START[rq]; t < DMB_HR_START[rq + 1]; ++t) {
-            const int cq = DMB_HR_COL[t];
-            if (cq >= NVP) s += eb[EB_HNZ + DMB_HR_IDX[t]] * T[(cq - NVP) * TILE_LD + NY + a];
-          }
+        for (int t = DMB_HR_START[rq]; t < DMB_HR_START[rq + 1]; ++t) {
+          const int cq = DMB_HR_COL[t];
+          if (cq >= NVP) s += T[STG_HNZ + DMB_HR_IDX[t]] * T[(cq - NVP) * TILE_LD + NY + a];
+        }
         if (rq >= NVP) {
-          s += eb[EB_SIGY + rq - NVP] * T[(rq - NVP) * TILE_LD + NY + a];
+          s += T[STG_SIGY + rq - NVP] * T[(rq - NVP) * TILE_LD + NY + a];
           T[(rq - NVP) * TILE_LD + TILE_M + a] = s;
         } else T[(NY + rq) * TILE_LD + a] = s;
       }
     }
     WARP_SYNC();
+    SUB_TICK(I, 3);
     if (act) {
       // ---- reduced blocks ---------------------------------------------------------------------------------------------
       for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) {
         const int a = idx / NVP, b = idx - a * NVP;
         double h = T[(NY + a) * TILE_LD + b] + T[(NY + b) * TILE_LD + a], yty = 0.0;
-        if (!ls_mode)
-          for (int t = DMB_HR_START[a]; t < DMB_HR_START[a + 1]; ++t) if (DMB_HR_COL[t] == b) h += eb[EB_HNZ + DMB_HR_IDX[t]];
+        for (int t = DMB_HR_START[a]; t < DMB_HR_START[a + 1]; ++t) if (DMB_HR_COL[t] == b) h += T[STG_HNZ + DMB_HR_IDX[t]];
+#pragma unroll 4
         for (int j = 0; j < NY; ++j) {
           const double yja = T[j * TILE_LD + NY + a];
           h += yja * T[j * TILE_LD + TILE_M + b];
@@ -494,35 +547,37 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
         er[ER_HH + idx] = h; er[ER_YTY + idx] = yty;
       }
       for (int a = c.gl; a < NVP; a += GSZ) {
-        double g = eb[EB_GOBJ + a] + T[(NY + a) * TILE_LD + NVP], yy = 0.0;
+        double g = T[STG_GOBJ + a] + T[(NY + a) * TILE_LD + NVP], yy = 0.0;
+#pragma unroll 4
         for (int j = 0; j < NY; ++j) {
           const double yja = T[j * TILE_LD + NY + a];
-          g += yja * (eb[EB_GY + j] + T[j * TILE_LD + TILE_M + NVP]);
+          g += yja * (T[STG_GY + j] + T[j * TILE_LD + TILE_M + NVP]);
           yy += yja * T[j * TILE_LD + NY + NVP];
         }
         er[ER_GH + a] = g; er[ER_YTY0 + a] = yy;
       }
-      for (int idx = c.gl; idx < NX * NVP; idx += GSZ) er[ER_AB + idx] = T[DMB_XF_SEL[idx / NVP] * TILE_LD + NY + idx % NVP];
+      for (int idx = c.gl; idx < NX * NVP; idx += GSZ) { const int r = idx / NVP; er[ER_AB + idx] = T[DMB_XF_SEL[r] * TILE_LD + NY + idx - r * NVP]; }
       for (int i = c.gl; i < NX; i += GSZ)
         er[ER_B + i] = T[DMB_XF_SEL[i] * TILE_LD + NY + NVP] + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + i]);
     }
     WARP_SYNC();
+    SUB_TICK(I, 4);
 #if NNL > 0
     if (act) {
       // condensed inequality slacks: H += sum_i sig_i d_i d_i', g += sum_i d_i r_i, projected with t_i = T' d_i
       for (int i = 0; i < NNL; ++i) {
-        double* tv = T + (NY + NVP - 1) * TILE_LD + NE;       // scratch row tail (NVP + 1 entries)
+        double* tv = T + STG_DQ;                               // NE entries of scratch
         for (int a = c.gl; a < NE; a += GSZ) {
           double s = 0.0;
           for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) {
             const int cq = DMB_D_COL[t];
-            if (cq >= NVP) s += eb[EB_DNZ + t] * T[(cq - NVP) * TILE_LD + NY + a];
-            else if (cq == a) s += eb[EB_DNZ + t];
+            if (cq >= NVP) s += T[STG_DNZ + t] * T[(cq - NVP) * TILE_LD + NY + a];
+            else if (cq == a) s += T[STG_DNZ + t];
           }
           tv[a] = s;
         }
         WARP_SYNC();
-        const double sig = eb[EB_SIGS + i], rd = eb[EB_RD + i] + sig * tv[NVP];
+        const double sig = T[STG_SIGS + i], rd = T[STG_RD + i] + sig * tv[NVP];
         for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) er[ER_HH + idx] += sig * tv[idx / NVP] * tv[idx % NVP];
         for (int a = c.gl; a < NVP; a += GSZ) er[ER_GH + a] += tv[a] * rd;
         WARP_SYNC();
@@ -535,142 +590,134 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Riccati sweep over the tree, warp 0 (lanes over matrix entries); everything it touches is in shared
-// memory.  Qs: NV*NV + NV + NXI*NV.  v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
+// Riccati sweep over the scenario tree.  v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
+//  (1) all threads: node matrices Q0 = node terms (Sigma + delta, barrier gradient, rterm, mterm) + the
+//      projected edge Hessians of the children — everything that does not depend on a child's value function;
+//  (2) warp 0, backwards over the nodes, everything in shared memory, loops fully unrolled:
+//        W = P_c [A B]_aug , Q += [A B]_aug' W , Cholesky of Q_uu , K = -Q_uu^{-1} Q_u. , P = Q_xx + Q_xu K (in place).
 // *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV double ab_aug(const double* er, int r, int vi) {      // [A B] of the child state xi_c = (x_c, u_prev_c)
-  if (r < NX) {
-    if (vi < NX) return er[ER_AB + r * NVP + vi];
-    if (vi >= NXI) return er[ER_AB + r * NVP + (vi - NU)];
-    return 0.0;
-  }
-  return vi == NXI + (r - NX) ? 1.0 : 0.0;
-}
-
 DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
-  double* Q = Qs;                 // NV x NV
-  double* qv = Qs + NV * NV;      // NV
-  double* PA = qv + NV;           // NXI x NV  (P_child [A B])
   if (c.tid == 0) *flag = 0;
+  // ---- (1) node matrices ------------------------------------------------------------------------------------------
+  for (int idx = c.tid; idx < NNODE * (NV * NV + NV); idx += c.nthr) {
+    const int n = idx / (NV * NV + NV), ent = idx - n * (NV * NV + NV);
+    double* wn = I.node + (size_t)n * WN_NODE;
+    const int k = DMB_NODE_K[n];
+    const bool is_q = ent >= NV * NV;
+    const int a = is_q ? ent - NV * NV : ent / NV, b = is_q ? -1 : ent - (ent / NV) * NV;
+    // edge-local index of v-space position a / b (u_prev has none)
+    const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < 0 ? -1 : (b < NX ? b : (b >= NXI ? b - NU : -1));
+    double val = 0.0;
+    const bool exists = ia >= 0 && !(k == NHOR && ia >= NX);
+    if (exists && (is_q || a == b)) {
+      const int gi = NODE_OFF(n) + ia;
+      const double lo = I.lb[gi], hi = I.ub[gi], wx = I.w[gi];
+      const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
+      double sig = delta, gb = 0.0;
+      if (ls_mode) {
+        sig = 1.0;
+        if (hl) gb -= I.zL[gi];
+        if (hu) gb += I.zU[gi];
+      } else {
+        if (hl) { const double sl = wx - lo; sig += I.zL[gi] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
+        if (hu) { const double su = hi - wx; sig += I.zU[gi] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
+      }
+      val = is_q ? gb : sig;
+    }
+    if (k == NHOR) {
+      if (a < NX && (is_q || b < NX)) {
+        const int pe = DMB_NODE_PARENT_EDGE[n];
+        const double wgt = I.df * DMB_EDGE_OMEGA[pe];
+        if (is_q) { double gm[NX]; gen_mterm_grad(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm); val += wgt * gm[a]; }
+        else if (!ls_mode) { double hm[NX * NX]; gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm); val += wgt * hm[a * NX + b]; }
+      }
+    } else {
+      // rterm couples u (v-pos NXI..) and u_prev (v-pos NX..)
+      const int ra = (a >= NXI && a < NXI + NU) ? a - NXI : ((a >= NX && a < NXI) ? NU + a - NX : -1);
+      if (is_q) { if (ra >= 0) val += wn[WN_RG + ra]; }
+      else if (!ls_mode) {
+        const int rb = (b >= NXI && b < NXI + NU) ? b - NXI : ((b >= NX && b < NXI) ? NU + b - NX : -1);
+        if (ra >= 0 && rb >= 0) val += wn[WN_RH + ra * 2 * NU + rb];
+      }
+      if (ia >= 0 && (is_q || ib >= 0))
+        for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+          const double* eb = I.er + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * ER_SZ;
+          val += is_q ? eb[ER_GH + ia] + delta * eb[ER_YTY0 + ia] : eb[ER_HH + ia * NVP + ib] + delta * eb[ER_YTY + ia * NVP + ib];
+        }
+    }
+    wn[WN_Q + ent] = val;
+  }
   CTA_SYNC();
+  long long tsub_ = DMB_CLOCK();
+  // ---- (2) sweep ----------------------------------------------------------------------------------------------------------
   if (c.warp == 0) {
+    double* W = Qs;                  // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
+    double* pb = Qs + NXI * NVP;     // NXI       : p_c + P_c[:, x] b
     for (int n = NNODE - 1; n >= 0; --n) {
+      if (DMB_NODE_K[n] == NHOR) continue;
       double* wn = I.node + (size_t)n * WN_NODE;
-      const int k = DMB_NODE_K[n];
-      const double* wx = I.w + NODE_OFF(n);
-      for (int i = c.lane; i < NV * NV + NV; i += DMB_LANES) Q[i] = 0.0;
-      WARP_SYNC();
-      // node-level terms: Sigma + delta and barrier gradient on (x, u, eps); terminal cost; rterm (one lane)
-      for (int i = c.lane; i < NVP; i += DMB_LANES) {
-        if (k == NHOR && i >= NX) continue;
-        const int vi = i < NX ? i : i + NU;           // position in v-space
-        const int gi = NODE_OFF(n) + i;
-        const double lo = I.lb[gi], hi = I.ub[gi];
-        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
-        double sig = delta, gb = 0.0;
-        if (ls_mode) {
-          sig = 1.0;
-          if (hl) gb -= I.zL[gi];
-          if (hu) gb += I.zU[gi];
-        } else {
-          if (hl) { const double sl = wx[i] - lo; sig += I.zL[gi] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
-          if (hu) { const double su = hi - wx[i]; sig += I.zU[gi] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
-        }
-        Q[vi * NV + vi] = sig;
-        qv[vi] = gb;
-      }
-      WARP_SYNC();
-      if (k == NHOR) {
-        if (c.lane == 0) {
-          const int pe = DMB_NODE_PARENT_EDGE[n];
-          double gm[NX], hm[NX * NX];
-          gen_mterm_grad(wx, p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm);
-          gen_mterm_hess(wx, p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm);
-          const double wgt = I.df * DMB_EDGE_OMEGA[pe];
-          for (int a = 0; a < NX; ++a) {
-            qv[a] += wgt * gm[a];
-            if (!ls_mode) for (int b = 0; b < NX; ++b) Q[a * NV + b] += wgt * hm[a * NX + b];
-          }
-        }
-        WARP_SYNC();
-        for (int idx = c.lane; idx < NXI * NXI; idx += DMB_LANES) wn[WN_P + idx] = Q[(idx / NXI) * NV + idx % NXI];
-        for (int a = c.lane; a < NXI; a += DMB_LANES) wn[WN_PV + a] = qv[a];
-        WARP_SYNC();
-        continue;
-      }
-      if (c.lane == DMB_LANES - 1) {
-        double up[NU], gr[2 * NU], hr[4 * NU * NU];
-        for (int a = 0; a < NU; ++a) up[a] = node_uprev(I, I.w, n, a);
-        const double* tv = I.p + DMB_P_TVP + k * DMB_NTVP;
-        gen_rterm_grad(wx + NX, up, tv, gr);
-        gen_rterm_hess(wx + NX, up, tv, hr);
-        const double wgt = I.df * DMB_NODE_RW[n];
-        for (int a = 0; a < NU; ++a) {
-          qv[NXI + a] += wgt * gr[a];
-          qv[NX + a] += wgt * gr[NU + a];
-          if (!ls_mode) for (int b = 0; b < NU; ++b) {
-            Q[(NXI + a) * NV + NXI + b] += wgt * hr[a * 2 * NU + b];
-            Q[(NXI + a) * NV + NX + b] += wgt * hr[a * 2 * NU + NU + b];
-            Q[(NX + a) * NV + NXI + b] += wgt * hr[(NU + a) * 2 * NU + b];
-            Q[(NX + a) * NV + NX + b] += wgt * hr[(NU + a) * 2 * NU + NU + b];
-          }
-        }
-      }
-      WARP_SYNC();
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
         const double* er = I.er + (size_t)e * ER_SZ;
         const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
-        for (int idx = c.lane; idx < NXI * NV; idx += DMB_LANES) {
-          const int r = idx / NV, vi = idx - r * NV;
-          double a = 0.0;
+        for (int idx = c.lane; idx < NXI * NVP + NXI; idx += DMB_LANES) {
+          if (idx < NXI * NVP) {
+            const int r = idx / NVP, jj = idx - r * NVP;
+            double s = (jj >= NX && jj < NX + NU) ? P_AT(wc, r, NX + (jj - NX)) : 0.0;     // u_prev_c = u
 #pragma unroll
-          for (int t = 0; t < NXI; ++t) a += wc[WN_P + r * NXI + t] * ab_aug(er, t, vi);
-          PA[idx] = a;
+            for (int t = 0; t < NX; ++t) s += P_AT(wc, r, t) * er[ER_AB + t * NVP + jj];
+            W[idx] = s;
+          } else {
+            const int r = idx - NXI * NVP;
+            double s = wc[WN_QV + r];
+#pragma unroll
+            for (int t = 0; t < NX; ++t) s += P_AT(wc, r, t) * er[ER_B + t];
+            pb[r] = s;
+          }
         }
         WARP_SYNC();
-        for (int idx = c.lane; idx < NV * NV + NV; idx += DMB_LANES) {
-          if (idx < NV * NV) {
-            const int a = idx / NV, b = idx - a * NV;
-            double s = 0.0;
+        for (int idx = c.lane; idx < NVP * NVP + NVP; idx += DMB_LANES) {
+          if (idx < NVP * NVP) {
+            const int i = idx / NVP, jj = idx - i * NVP;
+            double s = (i >= NX && i < NX + NU) ? W[(NX + i - NX) * NVP + jj] : 0.0;
 #pragma unroll
-            for (int t = 0; t < NXI; ++t) s += ab_aug(er, t, a) * PA[t * NV + b];
-            const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < NX ? b : (b >= NXI ? b - NU : -1);
-            if (ia >= 0 && ib >= 0) s += er[ER_HH + ia * NVP + ib] + delta * er[ER_YTY + ia * NVP + ib];
-            Q[idx] += s;
+            for (int r = 0; r < NX; ++r) s += er[ER_AB + r * NVP + i] * W[r * NVP + jj];
+            wn[WN_Q + VPOS(i) * NV + VPOS(jj)] += s;
           } else {
-            const int a = idx - NV * NV;
-            double s = 0.0;
-            for (int t = 0; t < NXI; ++t) {
-              double pb = wc[WN_PV + t];
-              for (int r = 0; r < NX; ++r) pb += wc[WN_P + t * NXI + r] * er[ER_B + r];
-              s += ab_aug(er, t, a) * pb;
-            }
-            const int ia = a < NX ? a : (a >= NXI ? a - NU : -1);
-            if (ia >= 0) s += er[ER_GH + ia] + delta * er[ER_YTY0 + ia];
-            qv[a] += s;
+            const int i = idx - NVP * NVP;
+            double s = (i >= NX && i < NX + NU) ? pb[NX + i - NX] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NX; ++r) s += er[ER_AB + r * NVP + i] * pb[r];
+            wn[WN_QV + VPOS(i)] += s;
           }
         }
         WARP_SYNC();
       }
-      // eliminate the controls: every lane owns one column of [Q_ux | q_u] and solves with its own Cholesky of Q_uu
+      // eliminate the controls: every lane owns one column of [Q_u,xi | q_u] and carries its own Cholesky of Q_uu
       {
-        double L[NUT * NUT];
+        double L[NUT * NUT];              // unit-free Cholesky factor; the diagonal stores 1 / L_aa
         int bad = 0;
+#pragma unroll
         for (int a = 0; a < NUT; ++a)
+#pragma unroll
           for (int b = 0; b <= a; ++b) {
-            double s = Q[(NXI + a) * NV + NXI + b];
+            double s = wn[WN_Q + (NXI + a) * NV + NXI + b];
+#pragma unroll
             for (int t = 0; t < b; ++t) s -= L[a * NUT + t] * L[b * NUT + t];
-            if (a == b) { if (!(s > 0.0)) { bad = 1; s = 1.0; } L[a * NUT + a] = sqrt(s); }
-            else L[a * NUT + b] = s / L[b * NUT + b];
+            if (a == b) { if (!(s > 0.0)) { bad = 1; s = 1.0; } L[a * NUT + a] = rsqrt(s); }
+            else L[a * NUT + b] = s * L[b * NUT + b];
           }
         if (bad && c.lane == 0) *flag = 1;
         for (int col = c.lane; col <= NXI; col += DMB_LANES) {
           double rhs[NUT];
-          for (int a = 0; a < NUT; ++a) rhs[a] = col < NXI ? -Q[(NXI + a) * NV + col] : -qv[NXI + a];
-          for (int a = 0; a < NUT; ++a) { double s = rhs[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * rhs[t]; rhs[a] = s / L[a * NUT + a]; }
-          for (int a = NUT - 1; a >= 0; --a) { double s = rhs[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * rhs[t]; rhs[a] = s / L[a * NUT + a]; }
+#pragma unroll
+          for (int a = 0; a < NUT; ++a) rhs[a] = col < NXI ? -wn[WN_Q + (NXI + a) * NV + col] : -wn[WN_QV + NXI + a];
+#pragma unroll
+          for (int a = 0; a < NUT; ++a) { double s = rhs[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * rhs[t]; rhs[a] = s * L[a * NUT + a]; }
+#pragma unroll
+          for (int a = NUT - 1; a >= 0; --a) { double s = rhs[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * rhs[t]; rhs[a] = s * L[a * NUT + a]; }
+#pragma unroll
           for (int a = 0; a < NUT; ++a) { if (col < NXI) wn[WN_K + a * NXI + col] = rhs[a]; else wn[WN_KV + a] = rhs[a]; }
         }
       }
@@ -678,18 +725,21 @@ DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kap
       for (int idx = c.lane; idx < NXI * NXI + NXI; idx += DMB_LANES) {
         if (idx < NXI * NXI) {
           const int a = idx / NXI, b = idx - a * NXI;
-          double s = Q[a * NV + b];
-          for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_K + t * NXI + b];
-          wn[WN_P + idx] = s;
+          double s = wn[WN_Q + a * NV + b];
+#pragma unroll
+          for (int t = 0; t < NUT; ++t) s += wn[WN_Q + a * NV + NXI + t] * wn[WN_K + t * NXI + b];
+          wn[WN_Q + a * NV + b] = s;
         } else {
           const int a = idx - NXI * NXI;
-          double s = qv[a];
-          for (int t = 0; t < NUT; ++t) s += Q[a * NV + NXI + t] * wn[WN_KV + t];
-          wn[WN_PV + a] = s;
+          double s = wn[WN_QV + a];
+#pragma unroll
+          for (int t = 0; t < NUT; ++t) s += wn[WN_Q + a * NV + NXI + t] * wn[WN_KV + t];
+          wn[WN_QV + a] = s;
         }
       }
       WARP_SYNC();
     }
+    SUB_TICK(I, 5);
   }
   CTA_SYNC();
 }
@@ -699,6 +749,7 @@ DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kap
 // transposed LU solve in the group tile, inequality steps.
 // ---------------------------------------------------------------------------------------------------
 DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, double* tile_base) {
+  long long tsub_ = DMB_CLOCK();
   if (c.warp == 0) {
     for (int n = 0; n < NNODE; ++n) {
       double* wn = I.node + (size_t)n * WN_NODE;
@@ -734,37 +785,49 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
     }
     const double* w0 = I.node;
     for (int a = c.lane; a < NX; a += DMB_LANES) {
-      double s = w0[WN_PV + a];
-      for (int t = 0; t < NXI; ++t) s += w0[WN_P + a * NXI + t] * w0[WN_DXI + t];
+      double s = w0[WN_QV + a];
+      for (int t = 0; t < NXI; ++t) s += P_AT(w0, a, t) * w0[WN_DXI + t];
       I.lamn[a] = -s;
     }
+    SUB_TICK(I, 6);
   }
   CTA_SYNC();
   double* T = tile_base + (size_t)c.grp * TILE_SZ;
-  double* dq = T + NY * TILE_LD;            // scratch behind the LU copy: dq (NQ), then r (NY)
+  double* dq = T + STG_DQ;                  // dq (NQ), then r (NY), then jd (NNL)
   double* rv = dq + NQ;
   for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
     const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
     if (act) {
+      // stage LU, Yext and the sparse data of this edge (coalesced, independent loads)
+      for (int idx = c.gl; idx < NY * NY; idx += GSZ) { const int r = idx / NY; T[r * TILE_LD + idx - r * NY] = eb[EB_LU + idx]; }
+      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; T[r * TILE_LD + NY + idx - r * NE] = eb[EB_Y + idx]; }
+      for (int i = c.gl; i < DMB_NNZ_H; i += GSZ) T[STG_HNZ + i] = ls_mode ? 0.0 : eb[EB_HNZ + i];
+      for (int i = c.gl; i < NY; i += GSZ) { T[STG_GY + i] = eb[EB_GY + i]; T[STG_SIGY + i] = eb[EB_SIGY + i]; }
+#if NNL > 0
+      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
+      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = eb[EB_RD + i]; }
+#endif
       const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
-      for (int idx = c.gl; idx < NY * NY; idx += GSZ) T[(idx / NY) * TILE_LD + idx % NY] = eb[EB_LU + idx];
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];
-      for (int i = c.gl; i < NY; i += GSZ) {
-        double s = eb[EB_Y + i * NE + NVP];
-#pragma unroll
-        for (int t = 0; t < NVP; ++t) s += eb[EB_Y + i * NE + t] * dvp[t];
-        dq[NVP + i] = s;
-        I.dw[EDGE_OFF(e) + i] = s;
-      }
       // continuity multiplier = gradient of the child's cost-to-go
       const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
       for (int a = c.gl; a < NX; a += GSZ) {
-        double s = wc[WN_PV + a];
+        double s = wc[WN_QV + a];
 #pragma unroll
-        for (int t = 0; t < NXI; ++t) s += wc[WN_P + a * NXI + t] * wc[WN_DXI + t];
+        for (int t = 0; t < NXI; ++t) s += P_AT(wc, a, t) * wc[WN_DXI + t];
         I.lamn[LAM_EDGE(e) + NY + a] = s;
+      }
+    }
+    WARP_SYNC();
+    if (act) {
+      for (int i = c.gl; i < NY; i += GSZ) {
+        double s = T[i * TILE_LD + NY + NVP];
+#pragma unroll
+        for (int t = 0; t < NVP; ++t) s += T[i * TILE_LD + NY + t] * dq[t];
+        dq[NVP + i] = s;
+        I.dw[EDGE_OFF(e) + i] = s;
       }
     }
     WARP_SYNC();
@@ -773,11 +836,11 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
     if (act) {
       for (int i = c.gl; i < NNL; i += GSZ) {
         double s = 0.0;
-        for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) s += eb[EB_DNZ + t] * dq[DMB_D_COL[t]];
+        for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) s += T[STG_DNZ + t] * dq[DMB_D_COL[t]];
         jd[i] = s;
         I.ds[e * NNL + i] = s + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + NX + i]);
         // y_d+ = Sigma_s ds + grad_s phi = Sigma_s J dq + r_d
-        I.lamn[LAM_EDGE(e) + NY + NX + i] = eb[EB_SIGS + i] * s + eb[EB_RD + i];
+        I.lamn[LAM_EDGE(e) + NY + NX + i] = T[STG_SIGS + i] * s + T[STG_RD + i];
       }
     }
     WARP_SYNC();
@@ -785,11 +848,10 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
     if (act) {
       // r_y = -(g_y + [H_e dq]_y) - E' lam_C
       for (int j = c.gl; j < NY; j += GSZ) {
-        double s = eb[EB_GY + j] + (eb[EB_SIGY + j] + delta) * dq[NVP + j];
-        if (!ls_mode)
-          for (int t = DMB_HR_START[NVP + j]; t < DMB_HR_START[NVP + j + 1]; ++t) s += eb[EB_HNZ + DMB_HR_IDX[t]] * dq[DMB_HR_COL[t]];
+        double s = T[STG_GY + j] + (T[STG_SIGY + j] + delta) * dq[NVP + j];
+        for (int t = DMB_HR_START[NVP + j]; t < DMB_HR_START[NVP + j + 1]; ++t) s += T[STG_HNZ + DMB_HR_IDX[t]] * dq[DMB_HR_COL[t]];
 #if NNL > 0
-        for (int t = 0; t < DMB_NNZ_D; ++t) if (DMB_D_COL[t] == NVP + j) s += eb[EB_DNZ + t] * (eb[EB_SIGS + DMB_D_ROW[t]] * jd[DMB_D_ROW[t]] + eb[EB_RD + DMB_D_ROW[t]]);
+        for (int t = 0; t < DMB_NNZ_D; ++t) if (DMB_D_COL[t] == NVP + j) s += T[STG_DNZ + t] * (T[STG_SIGS + DMB_D_ROW[t]] * jd[DMB_D_ROW[t]] + T[STG_RD + DMB_D_ROW[t]]);
 #endif
         rv[j] = -s;
       }
@@ -799,11 +861,15 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
       for (int a = c.gl; a < NX; a += GSZ) rv[DMB_XF_SEL[a]] -= I.lamn[LAM_EDGE(e) + NY + a];
     }
     WARP_SYNC();
-    // ---- G_y' lam = r with P G_y = L U:  U' a = r ; L' b = a ; lam = P' b.  Column sweeps, lanes over rows ---------
+    // ---- G_y' lam = r with P G_y = L U (diagonal of U stored as reciprocal):  U' a = r ; L' b = a ; lam = P' b ----------
     for (int k = 0; k < NY; ++k) {
-      if (act && c.gl == 0) rv[k] /= T[k * TILE_LD + k];
+      double ak = 0.0;
+      if (act) {
+        ak = rv[k] * T[k * TILE_LD + k];
+        for (int r = k + 1 + c.gl; r < NY; r += GSZ) rv[r] -= T[k * TILE_LD + r] * ak;
+      }
       WARP_SYNC();
-      if (act) { const double ak = rv[k]; for (int r = k + 1 + c.gl; r < NY; r += GSZ) rv[r] -= T[k * TILE_LD + r] * ak; }
+      if (act && c.gl == 0) rv[k] = ak;
       WARP_SYNC();
     }
     for (int k = NY - 1; k >= 0; --k) {

@@ -10,10 +10,13 @@ struct DmbShared {          // small per-CTA state in shared memory
   int flag, fail;
 };
 
+#define DMB_NPHASE 17
 struct DmbResult {
   double f, mu, inf_pr, inf_du, df;
   int status, iters, n_resto;
+  long long phase_cycles[DMB_NPHASE];   // derivs | kkt+mu | factor | riccati | forward+recover | step sizes | line search | accept | init
 };
+#define DMB_TICK(ph) do { const long long t_ = DMB_CLOCK(); pc[ph] += t_ - t_last; t_last = t_; } while (0)
 
 DMB_DEV double ftb_step(double slack, double dslack, double tau) {   // largest a: slack + a*dslack >= (1-tau)*slack
   return dslack < 0.0 ? -tau * slack / dslack : 1.0;
@@ -72,6 +75,10 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
                             double* tile, double* Qs, DmbShared* S, DmbResult* out) {
   Inst I = I_in;
   double* red = S->red;
+  long long pc[DMB_NPHASE];
+  for (int i = 0; i < DMB_NPHASE; ++i) pc[i] = 0;
+  I.sub = c.tid == 0 ? pc + 9 : nullptr;
+  long long t_last = DMB_CLOCK();
   // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
   for (int i = c.tid; i < NWI; i += c.nthr) { I.w[i] = x0_internal[i]; I.zL[i] = 0.0; I.zU[i] = 0.0; }
   for (int i = c.tid; i < NLAM; i += c.nthr) { I.dc[i] = 1.0; I.lam[i] = 0.0; }
@@ -149,6 +156,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   }
   CTA_SYNC();
 
+  DMB_TICK(8);
   double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
   const double theta_max = o.theta_max_fact * fmax(1.0, theta), theta_min = o.theta_min_fact * fmax(1.0, theta);
   double delta_w_last = 0.0;
@@ -159,6 +167,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   while (true) {
     // ---- convergence tests ----------------------------------------------------------------------------------------------
     eval_derivatives(c, I);
+    DMB_TICK(0);
     double dual, cmpl, s_d, s_c;
     kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
     dual0 = dual;
@@ -190,10 +199,12 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
         CTA_SYNC();
       } else break;
     }
+    DMB_TICK(1);
     // ---- search direction ------------------------------------------------------------------------------------------------
     if (c.tid == 0) S->fail = 0;
     CTA_SYNC();
     factor_edges(c, I, I.res, mu, o.kappa_d, 0, tile, &S->fail);
+    DMB_TICK(2);
     double delta_w = 0.0;
     if (degenerate_reg) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
     bool step_fail = S->fail != 0;
@@ -206,7 +217,9 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     }
     if (step_fail) { status = DMB_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
+    DMB_TICK(3);
     forward_recover(c, I, I.res, delta_w, 0, tile);
+    DMB_TICK(4);
 
     // ---- step sizes, directional derivative (I.go = objective gradient, scaled by df) ------------------------------
     double a_max = 1.0, a_z = 1.0, dphi = 0.0;
@@ -244,6 +257,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     a_z = block_min(c, a_z, red);
     dphi = block_sum(c, dphi, red);
     const double phi = barrier_phi(c, I, I.w, I.s, mu, o.kappa_d, f, red);
+    DMB_TICK(5);
 
     // ---- filter line search -------------------------------------------------------------------------------------------------
     double a_min;
@@ -279,6 +293,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       // TODO(second-order correction): the oracle applies it on the first trial when theta grows; see DESIGN.md
       alpha *= o.alpha_red_factor;
     }
+    DMB_TICK(6);
     if (!accepted) {
       // restoration substitute is not implemented on the device: report like the oracle does when it fails
       ++n_resto;
@@ -322,11 +337,13 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     for (int i = c.tid; i < NLAM; i += c.nthr) { I.lam[i] += a_used * (I.lamn[i] - I.lam[i]); I.res[i] = I.rest[i]; }
     f = f_t; theta = theta_t; inf_pr = infpr_t;
     CTA_SYNC();
+    DMB_TICK(7);
     ++it;
   }
   if (c.tid == 0) {
     out->f = f / I.df; out->mu = mu; out->inf_pr = inf_pr; out->inf_du = dual0;
     out->status = status; out->iters = it; out->n_resto = n_resto; out->df = I.df;
+    for (int i = 0; i < DMB_NPHASE; ++i) out->phase_cycles[i] = pc[i];
   }
   CTA_SYNC();
 }

@@ -62,8 +62,12 @@ def launch_config(r: Recipe):
     if 8 * fixed > 220 * 1024:
         raise NotImplementedError(f"problem too large for the shared-memory resident solver ({8 * fixed} bytes per CTA)")
     vec_smem = int(8 * (fixed + vec) <= 113 * 1024)
+    if "DMB_FORCE_VEC_SMEM" in os.environ:                 # tuning experiments only
+        vec_smem = int(os.environ["DMB_FORCE_VEC_SMEM"])
     total = 8 * (fixed + (vec if vec_smem else 0)) + 1024
     min_ctas = max(1, min(4, (227 * 1024) // total))
+    if "DMB_FORCE_MIN_CTAS" in os.environ:
+        min_ctas = int(os.environ["DMB_FORCE_MIN_CTAS"])
     return threads, vec_smem, min_ctas
 
 

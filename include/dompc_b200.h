@@ -48,7 +48,8 @@ enum { DMB_DIM_NW = 0, DMB_DIM_NG, DMB_DIM_NP, DMB_DIM_NX, DMB_DIM_NU, DMB_DIM_N
        DMB_DIM_COUNT };
 
 /* per-instance statistics written by the solve calls: stats[b*DMB_NSTAT + k] */
-enum { DMB_STAT_MU = 0, DMB_STAT_INF_PR, DMB_STAT_INF_DU, DMB_STAT_OBJ_SCALE, DMB_NSTAT };
+enum { DMB_STAT_MU = 0, DMB_STAT_INF_PR, DMB_STAT_INF_DU, DMB_STAT_OBJ_SCALE,
+       DMB_STAT_PHASE0 /* 9 + 8 SM-clock cycle counters of the solver (sub)phases, see DmbResult */, DMB_NSTAT = DMB_STAT_PHASE0 + 17 };
 
 typedef struct dmb_solver dmb_solver;
 struct DmbOptions;   /* layout: do_mpc_b200/csrc/ipm_core.cuh, mirrored by do_mpc_b200/solver/options.py */

@@ -28,7 +28,7 @@ int hostsim_solve(int B, const double* x_init, const double* x0s, const double* 
     Inst I;
     bind_vectors(I, vec.data());
     I.er = er.data(); I.node = node.data(); I.eb = eb.data();
-    I.p = p + (size_t)b * DMB_NP; I.lb = lbI.data(); I.ub = ubI.data(); I.df = 1.0;
+    I.p = p + (size_t)b * DMB_NP; I.lb = lbI.data(); I.ub = ubI.data(); I.df = 1.0; I.sub = nullptr;
     I.relax_fac = opts->bound_relax_factor; I.relax_max = opts->constr_viol_tol;
     load_initial_guess(c, x_init ? x_init + (size_t)b * DMB_NW : nullptr, x0s ? x0s + (size_t)b * DMB_NX : nullptr,
                        u0s ? u0s + (size_t)b * DMB_NU : nullptr, z0s ? z0s + (size_t)b * DMB_NZ : nullptr, x0i.data());
