@@ -15,6 +15,9 @@
 #ifndef DMB_VEC_SMEM
 #define DMB_VEC_SMEM 1
 #endif
+#ifndef DMB_ERN_SMEM
+#define DMB_ERN_SMEM 1
+#endif
 #define DMB_NWARP (DMB_THREADS / 32)
 #define DMB_NGRP (DMB_THREADS / GSZ)
 #ifndef DMB_MIN_CTAS
@@ -26,12 +29,16 @@
 #define SM_TILE 0
 #define SM_QS (SM_TILE + DMB_NGRP * TILE_SZ)
 #define SM_ER (SM_QS + DMB_QS_SIZE)
+#define ERN_DOUBLES (NEDGE * ER_SZ + NNODE * WN_NODE)
 #define SM_NODE (SM_ER + NEDGE * ER_SZ)
-#define SM_VEC (SM_NODE + NNODE * WN_NODE)
+#define SM_VEC (SM_ER + (DMB_ERN_SMEM ? ERN_DOUBLES : 0))
 #define SM_DOUBLES (SM_VEC + (DMB_VEC_SMEM ? WV_END : 0))
 #define SM_BYTES (SM_DOUBLES * sizeof(double) + sizeof(DmbShared) + 16)
 // per-CTA global workspace slot: bulk per-edge data (+ the iterate vectors when they do not fit on chip)
-#define SLOT_DOUBLES ((DMB_VEC_SMEM ? 0 : WV_END) + NEDGE * EB_SZ)
+#define SLOT_VEC 0
+#define SLOT_ERN (SLOT_VEC + (DMB_VEC_SMEM ? 0 : WV_END))
+#define SLOT_EB (SLOT_ERN + (DMB_ERN_SMEM ? 0 : ERN_DOUBLES))
+#define SLOT_DOUBLES (SLOT_EB + NEDGE * EB_SZ)
 
 struct KernelArgs {
   int B;
@@ -51,8 +58,10 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
         (int)(threadIdx.x % GSZ), (int)(threadIdx.x / GSZ), (int)(blockDim.x / GSZ)};
   double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
   Inst I;
-  bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot);
-  I.er = sm + SM_ER; I.node = sm + SM_NODE; I.eb = slot + (DMB_VEC_SMEM ? 0 : WV_END);
+  bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot + SLOT_VEC);
+  I.er = DMB_ERN_SMEM ? sm + SM_ER : slot + SLOT_ERN;
+  I.node = I.er + (size_t)NEDGE * ER_SZ;
+  I.eb = slot + SLOT_EB;
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
   while (true) {

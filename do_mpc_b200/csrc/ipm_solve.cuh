@@ -3,6 +3,10 @@
 #pragma once
 #include "ipm_core.cuh"
 
+#ifdef DMB_HOSTSIM
+#include <stdio.h>
+static int dmb_hostsim_verbose = 0;
+#endif
 struct DmbShared {          // small per-CTA state in shared memory
   double red[40];           // reduction scratch
   double filt_theta[MAX_FILTER], filt_phi[MAX_FILTER];
@@ -172,6 +176,9 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
     dual0 = dual;
     const double E0 = fmax(fmax(dual / s_d, inf_pr), cmpl / s_c);
+#ifdef DMB_HOSTSIM
+    if (dmb_hostsim_verbose) printf("%4d f=% .10e inf_pr=%.2e inf_du=%.2e cmpl=%.2e lg(mu)=%5.1f E0=%.2e theta=%.3e nfilt=%d\n", it, f / I.df, inf_pr, dual, cmpl, log10(mu), E0, theta, S->n_filt);
+#endif
     {
       // unscaled secondary tolerances
       double pu = 0.0;
@@ -294,6 +301,9 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       alpha *= o.alpha_red_factor;
     }
     DMB_TICK(6);
+#ifdef DMB_HOSTSIM
+    if (dmb_hostsim_verbose) printf("     alpha=%.3e a_max=%.3e a_z=%.3e ls=%d dphi=%.3e phi=%.12e a_min=%.3e accepted=%d armijo=%d delta_w=%.1e\n", a_used, a_max, a_z, ls, dphi, phi, a_min, (int)accepted, (int)armijo, delta_w);
+#endif
     if (!accepted) {
       // restoration substitute is not implemented on the device: report like the oracle does when it fails
       ++n_resto;

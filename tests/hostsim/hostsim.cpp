@@ -13,6 +13,7 @@ void hostsim_dims(int* d) {
   d[7] = NWI; d[8] = NLAM; d[9] = (int)sizeof(DmbOptions);
 }
 void hostsim_default_options(DmbOptions* o) { dmb_fill_default_options(o); }
+void hostsim_set_verbose(int v) { dmb_hostsim_verbose = v; }
 
 // x_init: [B, n_w] flat scaled initial guess or NULL (then x0s/u0s/z0s broadcast); outputs may be NULL.
 int hostsim_solve(int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s, const double* p,

@@ -1,0 +1,62 @@
+"""Every model family of the reference's regression suite through the kernel's algorithm source (CPU emulation):
+discrete-time, multi-element collocation, scenario tree + soft constraints, DAE + hard nonlinear constraints + tvp.
+Compared with the reference's own IPOPT results (golden step 0 = cold start exactly as testing/test_*.py runs it)."""
+import numpy as np
+import pytest
+
+from conftest import HostSim
+from examples_common import EXAMPLES, golden, cold_start_inputs
+
+TOL = 1e-5          # |u0 - u0_ref| <= 1e-5 * u_scaling (north_star tolerance)
+
+
+@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "dip"])
+def test_cold_start_matches_reference_ipopt(name):
+    make, sizes = EXAMPLES[name]
+    mpc = make(); mpc.prepare_nlp(); r = mpc.recipe
+    assert (r.n_w, r.n_g, r.n_p) == sizes
+    g = golden(name)
+    sim = HostSim(mpc, name)
+    sim.o.max_iter = 500
+    P, x0s, u0s, z0s = cold_start_inputs(r, g)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    assert out["status"][0] == 0
+    dev = np.abs(out["u0_scaled"][0] - g["u"][0] / r.u_scaling).max()
+    assert dev < TOL, (name, dev)
+    # primal feasibility of the returned flat solution as the kernel reports it
+    assert np.abs(out["g"][0][np.isfinite(mpc.nlp_cons_lb)]).max() < 1e-7
+    ineq = ~np.isfinite(mpc.nlp_cons_lb)
+    if ineq.any():
+        assert (out["g"][0][ineq] - mpc.nlp_cons_ub[ineq]).max() < 1e-6 and out["lam_g"][0][ineq].min() > -1e-9
+
+
+def test_warm_started_closed_loop_steps_match_reference():
+    """Steps 1..4 of the regression run: parameters from the golden, initial guess = our previous solution
+    (the reference warm-starts from its previous solution, optimizer.py:741-742)."""
+    name = "batch_reactor"
+    make, _ = EXAMPLES[name]
+    mpc = make(); mpc.prepare_nlp(); r = mpc.recipe
+    g = golden(name)
+    sim = HostSim(mpc, name)
+    P, x0s, u0s, z0s = cold_start_inputs(r, g)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    for t in range(1, 5):
+        out = sim.solve(g["opt_p_num"][t][None, :], x_init=out["x"])
+        assert out["status"][0] == 0
+        assert np.abs(out["u0_scaled"][0] - g["u"][t] / r.u_scaling).max() < TOL
+
+
+def test_industrial_poly_solution_within_tolerance():
+    """Config #5's model: the solution agrees with the reference within tolerance; the final iterations run at the
+    double-precision noise floor of this badly scaled problem (objective ~1.7e4, Sigma ~1e12) and the status flag is
+    allowed to differ from IPOPT's (known limitation)."""
+    make, sizes = EXAMPLES["industrial_poly"]
+    mpc = make(); mpc.prepare_nlp(); r = mpc.recipe
+    assert (r.n_w, r.n_g, r.n_p) == sizes
+    g = golden("industrial_poly")
+    sim = HostSim(mpc, "industrial_poly")
+    sim.o.max_iter = 300
+    P, x0s, u0s, z0s = cold_start_inputs(r, g)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    assert np.abs(out["u0_scaled"][0] - g["u"][0] / r.u_scaling).max() < TOL
+    assert np.abs(out["g"][0]).max() < 1e-7
