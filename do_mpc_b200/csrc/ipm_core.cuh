@@ -30,12 +30,18 @@ struct Ctx { int tid, nthr, lane, warp, nwarp, gl, grp, ngrp; };
 
 #ifdef DMB_HOSTSIM
 #define DMB_DEV
+#define DMB_PHASE
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #define DMB_LANES 1
 #define CTA_SYNC() ((void)0)
 #define WARP_SYNC() ((void)0)
 #else
 #define DMB_DEV __device__ __forceinline__
+#ifdef DMB_NOINLINE_PHASES
+#define DMB_PHASE __device__ __noinline__
+#else
+#define DMB_PHASE __device__ __forceinline__
+#endif
 #define DMB_LANES 32
 #define CTA_SYNC() __syncthreads()
 #define WARP_SYNC() __syncwarp()
@@ -89,7 +95,7 @@ enum DmbStatus {
 #define NLAM (NX + NEDGE * NLE)
 #define LAM_EDGE(e) (NX + (e) * NLE)
 #define DMB_INF 1e19
-#define MAX_FILTER 64
+#define MAX_FILTER 32
 
 // lane groups: one group factorises one edge
 #ifdef DMB_HOSTSIM
@@ -97,22 +103,29 @@ enum DmbStatus {
 #else
 #define GSZ (NY <= 16 ? 16 : 32)
 #endif
-// LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], then NVP rows of N = H_vy*Yext, then a
+// LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], a compact NVP x NE block N = H_vy*Yext, and a
 // staging area for the bulk per-edge data (global loads never sit inside dependent inner loops)
 #define TILE_NC (NY + NE)
 #define TILE_M (NY + NE)
 #define TILE_LD ((NY + 2 * NE) | 1)                   // odd leading dimension: conflict-free 64-bit rows
-#define TILE_ROWS (NY + NVP)
-#define STG_HNZ (TILE_ROWS * TILE_LD)
-#define STG_GOBJ (STG_HNZ + DMB_NNZ_H)
-#define STG_GY (STG_GOBJ + NQ)
+#define STG_N (NY * TILE_LD)                           // N block, row-major NVP x NE
+#define STG_HNZ (STG_N + NVP * NE)
+#define STG_GY (STG_HNZ + DMB_NNZ_H)
 #define STG_SIGY (STG_GY + NY)
 #define STG_DNZ (STG_SIGY + NY)
 #define STG_SIGS (STG_DNZ + DMB_NNZ_D)
 #define STG_RD (STG_SIGS + NNL)
-#define STG_DQ (STG_RD + NNL)                          // recovery: dq (NQ), r (NY), jd (NNL)
-#define STG_INVD (STG_DQ + NQ + NY + NNL)              // reciprocal pivots (NY)
-#define TILE_SZ (STG_INVD + NY)
+#define STG_GOBJ (STG_RD + NNL)                        // factor phase: gobj (NQ), reciprocal pivots (NY), permutation (NY)
+#define STG_INVD (STG_GOBJ + NQ)
+#define STG_PERM (STG_INVD + NY)                       // perm[m] = original row of the m-th pivot (as doubles)
+#define STG_DQ STG_GOBJ                                // recovery phase re-uses that space: dq (NQ), r (NY), jd (NNL)
+#ifdef DMB_USE_REG_LU
+#define STG_PB (STG_PERM + NY)                         // double-buffered published pivot row (2 x TILE_NC)
+#define TILE_SZ (STG_PB + 2 * TILE_NC)
+#else
+#define TILE_SZ (STG_PERM + NY)
+#endif
+static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY >= NNL");
 
 // per-edge reduced data kept in shared memory (inputs of the Riccati sweep)
 #define ER_AB 0                                        // Y[xf rows] : NX x NVP
@@ -174,7 +187,13 @@ enum DmbStatus {
 #define DMB_CLOCK() clock64()
 #endif
 #define DMB_NSUB 8
+#ifdef DMB_PROFILE
 #define SUB_TICK(I, ph) do { if ((I).sub) { const long long t_ = DMB_CLOCK(); (I).sub[ph] += t_ - tsub_; tsub_ = t_; } } while (0)
+#define SUB_START() long long tsub_ = DMB_CLOCK()
+#else
+#define SUB_TICK(I, ph) ((void)0)
+#define SUB_START() ((void)0)
+#endif
 struct Inst {
   long long* sub;      // optional fine-grained cycle counters (thread 0 only), see SUB_TICK
   double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *res, *rest, *dc, *s, *st, *ds, *vU;
@@ -241,6 +260,28 @@ DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
 }
 #endif
 
+// batched copy: all loads of a lane are issued before the first store (the two pointers may alias for the
+// compiler, which otherwise serialises load -> store -> load through the memory latency)
+#ifdef DMB_NO_COPY_BATCH
+#define DMB_COPY_BATCH(N, GL, STRIDE, LOADEXPR, ...) \
+  do { for (int idx = (GL); idx < (N); idx += (STRIDE)) { const double val = (LOADEXPR); __VA_ARGS__; } } while (0)
+#else
+#define DMB_COPY_BATCH(N, GL, STRIDE, LOADEXPR, ...)                                   \
+  do {                                                                                      \
+    constexpr int n_it_ = ((N) + (STRIDE) - 1) / (STRIDE);                                  \
+    double tmp_[n_it_];                                                                     \
+    _Pragma("unroll") for (int it_ = 0; it_ < n_it_; ++it_) {                               \
+      const int idx = (GL) + it_ * (STRIDE);                                                \
+      tmp_[it_] = idx < (N) ? (LOADEXPR) : 0.0;                                             \
+    }                                                                                       \
+    _Pragma("unroll") for (int it_ = 0; it_ < n_it_; ++it_) {                               \
+      const int idx = (GL) + it_ * (STRIDE);                                                \
+      const double val = tmp_[it_];                                                         \
+      if (idx < (N)) { __VA_ARGS__; }                                                       \
+    }                                                                                       \
+  } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // gather of the edge-local vector q = (x_parent, u_parent, eps_parent, y_e) and its parameters
 // ---------------------------------------------------------------------------------------------------
@@ -274,7 +315,7 @@ DMB_DEV double nl_ub_relaxed(const Inst& I, int e, int i) {
 // residuals + objective at a point (w, s) -> res (scaled), objective (scaled by df), theta = ||res||_1.
 // One thread per edge for the generated code; all threads for the reductions.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void eval_point(const Ctx& c, const Inst& I, const double* w, const double* s, double* res,
+DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const double* s, double* res,
                         double* scratch, double* f_out, double* theta_out, double* infpr_out) {
   double f = 0.0;
   for (int e = c.tid; e < NEDGE; e += c.nthr) {
@@ -323,7 +364,7 @@ DMB_DEV void eval_point(const Ctx& c, const Inst& I, const double* w, const doub
 // objective (go) and of the Lagrangian without bound multipliers (gl) for every primal variable.
 // lam are the SCALED multipliers; the row scales dc are applied here.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
+DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
   const double* w = I.w;
   for (int e = c.tid; e < NEDGE; e += c.nthr) {
     double q[NQ], lg[NY > 0 ? NY : 1], ln[NNL > 0 ? NNL : 1];
@@ -411,10 +452,10 @@ DMB_DEV void eval_derivatives(const Ctx& c, const Inst& I) {
 // blocks for the Riccati sweep.  `res` supplies the right-hand side (ignored in ls_mode: zero).
 // ls_mode = least-squares multiplier estimate: Hessian := identity, gradient := grad f - zL + zU.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
-                          double* tile_base, int* fail) {
+DMB_PHASE void factor_edges_smem(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
+                               double* tile_base, int* fail) {
   double* T = tile_base + (size_t)c.grp * TILE_SZ;
-  long long tsub_ = DMB_CLOCK();
+  SUB_START();
   for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
@@ -422,10 +463,10 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
     double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
     const double* dc = I.dc + LAM_EDGE(act ? e : 0);
     if (act) {
-      for (int i = c.gl; i < TILE_ROWS * TILE_LD; i += GSZ) T[i] = 0.0;
+      for (int i = c.gl; i < NY * TILE_LD; i += GSZ) T[i] = 0.0;
       // stage the bulk data of this edge (coalesced, independent loads)
-      for (int i = c.gl; i < DMB_NNZ_H; i += GSZ) T[STG_HNZ + i] = ls_mode ? 0.0 : eb[EB_HNZ + i];
-      for (int i = c.gl; i < NQ; i += GSZ) T[STG_GOBJ + i] = eb[EB_GOBJ + i];
+      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
+      DMB_COPY_BATCH(NQ, c.gl, GSZ, eb[EB_GOBJ + idx], T[STG_GOBJ + idx] = val);
 #if NNL > 0
       for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
 #endif
@@ -433,10 +474,8 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
     WARP_SYNC();
     if (act) {
       // Jacobian nonzeros (row scaled) -> tile columns [G_y | G_vp]; right-hand side -res
-      for (int k = c.gl; k < DMB_NNZ_J; k += GSZ) {
-        const int r = DMB_J_ROW[k], cq = DMB_J_COL[k];
-        T[r * TILE_LD + (cq >= NVP ? cq - NVP : NY + cq)] = dc[r] * eb[EB_JNZ + k];
-      }
+      DMB_COPY_BATCH(DMB_NNZ_J, c.gl, GSZ, eb[EB_JNZ + idx],
+                     const int r = DMB_J_ROW[idx]; const int cq = DMB_J_COL[idx]; T[r * TILE_LD + (cq >= NVP ? cq - NVP : NY + cq)] = dc[r] * val);
       for (int r = c.gl; r < NY; r += GSZ) {
         T[r * TILE_LD + NY + NVP] = ls_mode ? 0.0 : -res[LAM_EDGE(e) + r];
         // barrier terms of the edge unknowns y
@@ -480,7 +519,10 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
           const double t = T[k * TILE_LD + cc]; T[k * TILE_LD + cc] = T[pr * TILE_LD + cc]; T[pr * TILE_LD + cc] = t;
         }
       }
-      if (act && c.gl == 0) eb[EB_PIV + k] = (double)pr;
+      if (act && c.gl == 0) {
+        if (k == 0) for (int i = 0; i < NY; ++i) T[STG_PERM + i] = (double)i;
+        const double t = T[STG_PERM + k]; T[STG_PERM + k] = T[STG_PERM + pr]; T[STG_PERM + pr] = t;
+      }
       WARP_SYNC();
       if (act) {
         const double pv = T[k * TILE_LD + k];
@@ -498,6 +540,7 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
     }
     SUB_TICK(I, 1);
     if (act) {
+      for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
       for (int idx = c.gl; idx < NY * NY; idx += GSZ) {
         const int r = idx / NY, cc = idx - r * NY;
         eb[EB_LU + idx] = r == cc ? T[STG_INVD + r] : T[r * TILE_LD + cc];
@@ -527,7 +570,7 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
         if (rq >= NVP) {
           s += T[STG_SIGY + rq - NVP] * T[(rq - NVP) * TILE_LD + NY + a];
           T[(rq - NVP) * TILE_LD + TILE_M + a] = s;
-        } else T[(NY + rq) * TILE_LD + a] = s;
+        } else T[STG_N + rq * NE + a] = s;
       }
     }
     WARP_SYNC();
@@ -536,7 +579,7 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
       // ---- reduced blocks ---------------------------------------------------------------------------------------------
       for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) {
         const int a = idx / NVP, b = idx - a * NVP;
-        double h = T[(NY + a) * TILE_LD + b] + T[(NY + b) * TILE_LD + a], yty = 0.0;
+        double h = T[STG_N + a * NE + b] + T[STG_N + b * NE + a], yty = 0.0;
         for (int t = DMB_HR_START[a]; t < DMB_HR_START[a + 1]; ++t) if (DMB_HR_COL[t] == b) h += T[STG_HNZ + DMB_HR_IDX[t]];
 #pragma unroll 4
         for (int j = 0; j < NY; ++j) {
@@ -547,7 +590,7 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
         er[ER_HH + idx] = h; er[ER_YTY + idx] = yty;
       }
       for (int a = c.gl; a < NVP; a += GSZ) {
-        double g = T[STG_GOBJ + a] + T[(NY + a) * TILE_LD + NVP], yy = 0.0;
+        double g = T[STG_GOBJ + a] + T[STG_N + a * NE + NVP], yy = 0.0;
 #pragma unroll 4
         for (int j = 0; j < NY; ++j) {
           const double yja = T[j * TILE_LD + NY + a];
@@ -589,6 +632,215 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
   CTA_SYNC();
 }
 
+#if !defined(DMB_HOSTSIM) && (DMB_NY <= 32) && defined(DMB_USE_REG_LU)
+#define DMB_HAVE_REG_LU 1
+// ---------------------------------------------------------------------------------------------------
+// Register-resident variant of the factor phase (device only, one row per lane): every lane keeps its row of
+// [G_y | G_vp | rhs] in registers; per pivot step only the pivot row is published through shared memory.
+// Written after ncu capture r1b / the cycle counters showed the shared-memory version spending ~1.5k cycles per
+// pivot step in store->load dependent chains.  Same numerics (partial pivoting, reciprocal pivots).
+// ---------------------------------------------------------------------------------------------------
+DMB_PHASE void factor_edges_reg(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
+                              double* tile_base, int* fail) {
+  double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  SUB_START();
+  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
+    const int e = e0 + c.grp;
+    const bool act = e < NEDGE;
+    double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+    double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
+    const double* dc = I.dc + LAM_EDGE(act ? e : 0);
+    if (act) {
+      for (int i = c.gl; i < NY * TILE_LD; i += GSZ) T[i] = 0.0;
+      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
+      DMB_COPY_BATCH(NQ, c.gl, GSZ, eb[EB_GOBJ + idx], T[STG_GOBJ + idx] = val);
+#if NNL > 0
+      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
+#endif
+    }
+    WARP_SYNC();
+    if (act) {
+      DMB_COPY_BATCH(DMB_NNZ_J, c.gl, GSZ, eb[EB_JNZ + idx],
+                     const int r = DMB_J_ROW[idx]; const int cq = DMB_J_COL[idx]; T[r * TILE_LD + (cq >= NVP ? cq - NVP : NY + cq)] = dc[r] * val);
+      for (int r = c.gl; r < NY; r += GSZ) {
+        T[r * TILE_LD + NY + NVP] = ls_mode ? 0.0 : -res[LAM_EDGE(e) + r];
+        const int i = EDGE_OFF(e) + r;
+        const double lo = I.lb[i], hi = I.ub[i], wy = I.w[i];
+        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
+        double sig = 0.0, gb = 0.0;
+        if (ls_mode) {
+          sig = 1.0;
+          if (hl) gb -= I.zL[i];
+          if (hu) gb += I.zU[i];
+        } else {
+          if (hl) { const double rs = 1.0 / (wy - lo); sig += I.zL[i] * rs; gb -= mu * rs; if (!hu) gb += kappa_d * mu; }
+          if (hu) { const double rs = 1.0 / (hi - wy); sig += I.zU[i] * rs; gb += mu * rs; if (!hl) gb -= kappa_d * mu; }
+        }
+        T[STG_SIGY + r] = sig;
+        T[STG_GY + r] = T[STG_GOBJ + NVP + r] + gb;
+        eb[EB_SIGY + r] = sig;
+        eb[EB_GY + r] = T[STG_GY + r];
+      }
+#if NNL > 0
+      for (int i = c.gl; i < NNL; i += GSZ) {
+        const double sl = nl_ub_relaxed(I, e, i) - I.s[e * NNL + i];
+        const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
+        const double rd = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
+        T[STG_SIGS + i] = sig; T[STG_RD + i] = rd;
+        eb[EB_SIGS + i] = sig; eb[EB_RD + i] = rd;
+      }
+#endif
+    }
+    WARP_SYNC();
+    SUB_TICK(I, 0);
+    // ---- LU, rows in registers ------------------------------------------------------------------------------------------
+    const bool has_row = act && c.gl < NY;
+    double a[TILE_NC];
+#pragma unroll
+    for (int cc = 0; cc < TILE_NC; ++cc) a[cc] = has_row ? T[c.gl * TILE_LD + cc] : 0.0;
+    int rank = has_row ? -1 : NY;
+    WARP_SYNC();
+#pragma unroll
+    for (int k = 0; k < NY; ++k) {
+      const int pr = group_argmax(c, rank == -1 ? fabs(a[k]) : -1.0, rank == -1 ? c.gl : -1);
+      double* pbk = T + STG_PB + (k & 1) * TILE_NC;
+      if (act && c.gl == pr) {
+        rank = k;
+        T[STG_PERM + k] = (double)c.gl;
+#pragma unroll
+        for (int cc = k; cc < TILE_NC; ++cc) pbk[cc] = a[cc];
+      }
+      WARP_SYNC();
+      if (act) {
+        const double pv = pbk[k];
+        if (!(fabs(pv) > 1e-300)) *fail = 1;
+        const double inv = 1.0 / pv;
+        if (rank == -1) {
+          const double l = a[k] * inv;
+          a[k] = l;
+#pragma unroll
+          for (int cc = k + 1; cc < TILE_NC; ++cc) a[cc] -= l * pbk[cc];
+        }
+        if (c.gl == 0) T[STG_INVD + k] = inv;
+      }
+    }
+    // rows back to the tile in pivot order
+    if (has_row) {
+#pragma unroll
+      for (int cc = 0; cc < TILE_NC; ++cc) T[rank * TILE_LD + cc] = a[cc];
+    }
+    WARP_SYNC();
+    SUB_TICK(I, 1);
+    // ---- back substitution: one lane per right-hand side, solution column in registers ----------------------------
+    const int j = c.gl;
+    const bool has_col = act && j < NE;
+    double x[NY];
+    if (has_col) {
+#pragma unroll
+      for (int k = NY - 1; k >= 0; --k) {
+        double sx = T[k * TILE_LD + NY + j];
+#pragma unroll
+        for (int cc = k + 1; cc < NY; ++cc) sx -= T[k * TILE_LD + cc] * x[cc];
+        x[k] = sx * T[STG_INVD + k];
+      }
+      if (j < NVP) {
+#pragma unroll
+        for (int k = 0; k < NY; ++k) x[k] = -x[k];
+      }
+    }
+    WARP_SYNC();          // everybody finished reading the eliminated right-hand sides
+    if (has_col) {
+#pragma unroll
+      for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = x[k];
+    }
+    if (act) {
+      for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
+      for (int idx = c.gl; idx < NY * NY; idx += GSZ) {
+        const int r = idx / NY, cc = idx - r * NY;
+        eb[EB_LU + idx] = r == cc ? T[STG_INVD + r] : T[r * TILE_LD + cc];
+      }
+    }
+    WARP_SYNC();
+    SUB_TICK(I, 2);
+    // ---- z = H_e t with t = column j of [I; Yext] (generated straight-line), then the reduced column ---------------
+    double z[NQ];
+    if (has_col) {
+      double t[NQ];
+#pragma unroll
+      for (int i = 0; i < NVP; ++i) t[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < NY; ++k) t[NVP + k] = x[k];
+      gen_hmul(T + STG_HNZ, t, z);
+#pragma unroll
+      for (int k = 0; k < NY; ++k) z[NVP + k] += T[STG_SIGY + k] * x[k];
+      if (j == NVP) {           // right-hand-side column: add the gradient
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) z[i] += T[STG_GOBJ + i];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) z[NVP + k] += T[STG_GY + k];
+      }
+    }
+    if (act) {
+      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; eb[EB_Y + idx] = T[r * TILE_LD + NY + idx - r * NE]; }
+    }
+    SUB_TICK(I, 3);
+    if (has_col) {
+#pragma unroll
+      for (int b = 0; b < NVP; ++b) {
+        double hh = z[b], yty = 0.0;
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+          const double ykb = T[k * TILE_LD + NY + b];
+          hh += ykb * z[NVP + k];
+          yty += ykb * x[k];
+        }
+        if (j < NVP) { er[ER_HH + b * NVP + j] = hh; er[ER_YTY + b * NVP + j] = yty; }
+        else { er[ER_GH + b] = hh; er[ER_YTY0 + b] = yty; }
+      }
+    }
+    if (act) {
+      for (int idx = c.gl; idx < NX * NVP; idx += GSZ) { const int r = idx / NVP; er[ER_AB + idx] = T[DMB_XF_SEL[r] * TILE_LD + NY + idx - r * NVP]; }
+      for (int i = c.gl; i < NX; i += GSZ)
+        er[ER_B + i] = T[DMB_XF_SEL[i] * TILE_LD + NY + NVP] + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + i]);
+    }
+    WARP_SYNC();
+    SUB_TICK(I, 4);
+#if NNL > 0
+    if (act) {
+      for (int i = 0; i < NNL; ++i) {
+        double* tv = T + STG_DQ;
+        for (int aa = c.gl; aa < NE; aa += GSZ) {
+          double sd = 0.0;
+          for (int tt = DMB_DR_START[i]; tt < DMB_DR_START[i + 1]; ++tt) {
+            const int cq = DMB_D_COL[tt];
+            if (cq >= NVP) sd += T[STG_DNZ + tt] * T[(cq - NVP) * TILE_LD + NY + aa];
+            else if (cq == aa) sd += T[STG_DNZ + tt];
+          }
+          tv[aa] = sd;
+        }
+        WARP_SYNC();
+        const double sig = T[STG_SIGS + i], rd = T[STG_RD + i] + sig * tv[NVP];
+        for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) er[ER_HH + idx] += sig * tv[idx / NVP] * tv[idx % NVP];
+        for (int aa = c.gl; aa < NVP; aa += GSZ) er[ER_GH + aa] += tv[aa] * rd;
+        WARP_SYNC();
+      }
+    }
+    WARP_SYNC();
+#endif
+  }
+  CTA_SYNC();
+}
+#endif
+
+DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
+                          double* tile_base, int* fail) {
+#ifdef DMB_HAVE_REG_LU
+  factor_edges_reg(c, I, res, mu, kappa_d, ls_mode, tile_base, fail);
+#else
+  factor_edges_smem(c, I, res, mu, kappa_d, ls_mode, tile_base, fail);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Riccati sweep over the scenario tree.  v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
 //  (1) all threads: node matrices Q0 = node terms (Sigma + delta, barrier gradient, rterm, mterm) + the
@@ -597,7 +849,8 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 //        W = P_c [A B]_aug , Q += [A B]_aug' W , Cholesky of Q_uu , K = -Q_uu^{-1} Q_u. , P = Q_xx + Q_xu K (in place).
 // *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
+DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
+  CTA_SYNC();                       // every thread has consumed the flag of a previous call before it is reset
   if (c.tid == 0) *flag = 0;
   // ---- (1) node matrices ------------------------------------------------------------------------------------------
   for (int idx = c.tid; idx < NNODE * (NV * NV + NV); idx += c.nthr) {
@@ -649,7 +902,7 @@ DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kap
     wn[WN_Q + ent] = val;
   }
   CTA_SYNC();
-  long long tsub_ = DMB_CLOCK();
+  SUB_START();
   // ---- (2) sweep ----------------------------------------------------------------------------------------------------------
   if (c.warp == 0) {
     double* W = Qs;                  // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
@@ -748,8 +1001,8 @@ DMB_DEV void riccati_backward(const Ctx& c, const Inst& I, double mu, double kap
 // forward roll-out (warp 0) then, per edge by its lane group: dy = Yext [dv; 1], new multipliers by a
 // transposed LU solve in the group tile, inequality steps.
 // ---------------------------------------------------------------------------------------------------
-DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, double* tile_base) {
-  long long tsub_ = DMB_CLOCK();
+DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, double* tile_base) {
+  SUB_START();
   if (c.warp == 0) {
     for (int n = 0; n < NNODE; ++n) {
       double* wn = I.node + (size_t)n * WN_NODE;
@@ -801,10 +1054,11 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
     const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
     if (act) {
       // stage LU, Yext and the sparse data of this edge (coalesced, independent loads)
-      for (int idx = c.gl; idx < NY * NY; idx += GSZ) { const int r = idx / NY; T[r * TILE_LD + idx - r * NY] = eb[EB_LU + idx]; }
-      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; T[r * TILE_LD + NY + idx - r * NE] = eb[EB_Y + idx]; }
-      for (int i = c.gl; i < DMB_NNZ_H; i += GSZ) T[STG_HNZ + i] = ls_mode ? 0.0 : eb[EB_HNZ + i];
-      for (int i = c.gl; i < NY; i += GSZ) { T[STG_GY + i] = eb[EB_GY + i]; T[STG_SIGY + i] = eb[EB_SIGY + i]; }
+      DMB_COPY_BATCH(NY * NY, c.gl, GSZ, eb[EB_LU + idx], T[(idx / NY) * TILE_LD + idx % NY] = val);
+      DMB_COPY_BATCH(NY * NE, c.gl, GSZ, eb[EB_Y + idx], T[(idx / NE) * TILE_LD + NY + idx % NE] = val);
+      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_GY + idx], T[STG_GY + idx] = val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
 #if NNL > 0
       for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
       for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = eb[EB_RD + i]; }
@@ -876,14 +1130,7 @@ DMB_DEV void forward_recover(const Ctx& c, const Inst& I, const double* res, dou
       if (act) { const double bk = rv[k]; for (int r = c.gl; r < k; r += GSZ) rv[r] -= T[k * TILE_LD + r] * bk; }
       WARP_SYNC();
     }
-    if (act && c.gl == 0) {
-      for (int k = NY - 1; k >= 0; --k) {
-        const int pr = (int)eb[EB_PIV + k];
-        if (pr != k) { const double t = rv[k]; rv[k] = rv[pr]; rv[pr] = t; }
-      }
-    }
-    WARP_SYNC();
-    if (act) for (int j = c.gl; j < NY; j += GSZ) I.lamn[LAM_EDGE(e) + j] = rv[j];
+    if (act) for (int j = c.gl; j < NY; j += GSZ) I.lamn[LAM_EDGE(e) + (int)eb[EB_PIV + j]] = rv[j];      // lam = P' b
     WARP_SYNC();
   }
   CTA_SYNC();

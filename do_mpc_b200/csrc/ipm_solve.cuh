@@ -20,7 +20,11 @@ struct DmbResult {
   int status, iters, n_resto;
   long long phase_cycles[DMB_NPHASE];   // derivs | kkt+mu | factor | riccati | forward+recover | step sizes | line search | accept | init
 };
+#ifdef DMB_PROFILE
 #define DMB_TICK(ph) do { const long long t_ = DMB_CLOCK(); pc[ph] += t_ - t_last; t_last = t_; } while (0)
+#else
+#define DMB_TICK(ph) ((void)0)
+#endif
 
 DMB_DEV double ftb_step(double slack, double dslack, double tau) {   // largest a: slack + a*dslack >= (1-tau)*slack
   return dslack < 0.0 ? -tau * slack / dslack : 1.0;
@@ -79,10 +83,14 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
                             double* tile, double* Qs, DmbShared* S, DmbResult* out) {
   Inst I = I_in;
   double* red = S->red;
+#ifdef DMB_PROFILE
   long long pc[DMB_NPHASE];
   for (int i = 0; i < DMB_NPHASE; ++i) pc[i] = 0;
   I.sub = c.tid == 0 ? pc + 9 : nullptr;
   long long t_last = DMB_CLOCK();
+#else
+  I.sub = nullptr;
+#endif
   // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
   for (int i = c.tid; i < NWI; i += c.nthr) { I.w[i] = x0_internal[i]; I.zL[i] = 0.0; I.zU[i] = 0.0; }
   for (int i = c.tid; i < NLAM; i += c.nthr) { I.dc[i] = 1.0; I.lam[i] = 0.0; }
@@ -217,7 +225,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     bool step_fail = S->fail != 0;
     while (!step_fail) {
       riccati_backward(c, I, mu, o.kappa_d, delta_w, 0, Qs, &S->flag);
-      if (!S->flag) break;
+      const int wrong_inertia = S->flag;      // (re-set only behind the barrier at the top of the next call)
+      if (!wrong_inertia) break;
       if (delta_w == 0.0) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
       else delta_w *= (delta_w_last == 0.0 ? o.kappa_w_plus_first : o.kappa_w_plus);
       if (delta_w > o.delta_w_max) step_fail = true;
@@ -353,7 +362,11 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   if (c.tid == 0) {
     out->f = f / I.df; out->mu = mu; out->inf_pr = inf_pr; out->inf_du = dual0;
     out->status = status; out->iters = it; out->n_resto = n_resto; out->df = I.df;
+#ifdef DMB_PROFILE
     for (int i = 0; i < DMB_NPHASE; ++i) out->phase_cycles[i] = pc[i];
+#else
+    for (int i = 0; i < DMB_NPHASE; ++i) out->phase_cycles[i] = 0;
+#endif
   }
   CTA_SYNC();
 }

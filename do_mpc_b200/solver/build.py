@@ -44,7 +44,7 @@ def _sizes(r: Recipe, src: str, threads: int):
     nv = nxi + nut
     n_node, n_edge = len(r.node_k), len(r.edge_k)
     gsz = 16 if ny <= 16 else 32
-    tile = (ny + nvp) * ((ny + 2 * ne) | 1) + nnz_h + nnz_d + 2 * nq + 4 * ny + 3 * nnl
+    tile = ny * ((ny + 2 * ne) | 1) + nvp * ne + nnz_h + nnz_d + nq + 4 * ny + 2 * nnl
     tiles = (threads // gsz) * tile
     qs = nxi * nvp + nxi + 8
     ern = n_edge * (nx * nvp + nx + 2 * nvp * nvp + 2 * nvp) + n_node * (nv * nv + nv + nut * nxi + nut + nxi + 2 * nu + 4 * nu * nu)
@@ -67,7 +67,7 @@ def launch_config(r: Recipe, src: str):
         raise NotImplementedError(f"problem too large for the shared-memory tiles of the solver ({8 * fixed} bytes per CTA)")
     kb = lambda d: 8 * d / 1024.0
     ern_smem = int(kb(fixed + ern) <= 110)
-    vec_smem = int(ern_smem and kb(fixed + ern + vec) <= 74)
+    vec_smem = int(ern_smem and kb(fixed + ern + vec) <= 73)
     if "DMB_FORCE_VEC_SMEM" in os.environ:                 # tuning experiments only
         vec_smem = int(os.environ["DMB_FORCE_VEC_SMEM"])
     total = kb(fixed + (ern if ern_smem else 0) + (vec if vec_smem else 0)) + 1
@@ -80,7 +80,8 @@ def launch_config(r: Recipe, src: str):
 def build_library(r: Recipe, verbose: bool = False) -> Path:
     src = generate(r)
     threads, ern_smem, vec_smem, min_ctas = launch_config(r, src)
-    key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{ern_smem}{vec_smem}{min_ctas}").encode()).hexdigest()[:16]
+    extra = os.environ.get("DMB_EXTRA_NVCC_FLAGS", "").split()          # tuning experiments only
+    key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{ern_smem}{vec_smem}{min_ctas}{extra}").encode()).hexdigest()[:16]
     d = CACHE / key
     lib = d / f"libdmb_{key}.so"
     if lib.exists():
@@ -88,7 +89,7 @@ def build_library(r: Recipe, verbose: bool = False) -> Path:
     d.mkdir(parents=True, exist_ok=True)
     (d / "problem_gen.h").write_text(src)
     cmd = [NVCC, *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-           f"-DDMB_THREADS={threads}", f"-DDMB_ERN_SMEM={ern_smem}", f"-DDMB_VEC_SMEM={vec_smem}", f"-DDMB_MIN_CTAS={min_ctas}", f"-I{d}", f"-I{CSRC}", f"-I{INCLUDE}",
+           f"-DDMB_THREADS={threads}", f"-DDMB_ERN_SMEM={ern_smem}", f"-DDMB_VEC_SMEM={vec_smem}", f"-DDMB_MIN_CTAS={min_ctas}", *extra, f"-I{d}", f"-I{CSRC}", f"-I{INCLUDE}",
            str(CSRC / "dmb_api.cu"), "-o", str(lib) + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

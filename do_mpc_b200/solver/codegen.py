@@ -130,6 +130,14 @@ def generate(r: Recipe) -> str:
     for r_ in dr: dr_start[r_ + 1] += 1
     for i in range(n_nl): dr_start[i + 1] += dr_start[i]
 
+    # ---- H_e * v with the static sparsity of the edge Hessian (straight-line; hnz = lower-triangle nonzeros) ----------
+    lines = []
+    for i in range(n_q):
+        terms = [f"hnz[{k}] * v[{c_}]" for (c_, k) in sorted(hrows[i])]
+        lines.append(f"  out[{i}] = " + (" + ".join(terms) if terms else "0.0") + ";")
+    out.append(_fn("gen_hmul", "const double* __restrict__ hnz, const double* __restrict__ v, double* __restrict__ out",
+                   "  (void)hnz; (void)v;\n" + "\n".join(lines)))
+
     # ---- rterm (u, u_prev, tvp) ------------------------------------------------------------------------------------------
     inpR = {}
     for i, s in enumerate(u_ids): inpR[s] = f"u[{i}]"
