@@ -269,7 +269,7 @@ DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
 #define DMB_COPY_BATCH(N, GL, STRIDE, LOADEXPR, ...)                                   \
   do {                                                                                      \
     constexpr int n_it_ = ((N) + (STRIDE) - 1) / (STRIDE);                                  \
-    double tmp_[n_it_];                                                                     \
+    double tmp_[n_it_ > 0 ? n_it_ : 1];                                                                  \
     _Pragma("unroll") for (int it_ = 0; it_ < n_it_; ++it_) {                               \
       const int idx = (GL) + it_ * (STRIDE);                                                \
       tmp_[it_] = idx < (N) ? (LOADEXPR) : 0.0;                                             \

@@ -309,6 +309,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       // TODO(second-order correction): the oracle applies it on the first trial when theta grows; see DESIGN.md
       alpha *= o.alpha_red_factor;
     }
+    CTA_SYNC();                     // all threads are done reading the filter before thread 0 augments it
     DMB_TICK(6);
 #ifdef DMB_HOSTSIM
     if (dmb_hostsim_verbose) printf("     alpha=%.3e a_max=%.3e a_z=%.3e ls=%d dphi=%.3e phi=%.12e a_min=%.3e accepted=%d armijo=%d delta_w=%.1e\n", a_used, a_max, a_z, ls, dphi, phi, a_min, (int)accepted, (int)armijo, delta_w);
