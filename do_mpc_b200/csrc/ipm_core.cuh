@@ -59,8 +59,8 @@ struct DmbOptions {
   double alpha_red_factor, eta_phi, theta_max_fact, theta_min_fact, s_phi, s_theta, gamma_phi, gamma_theta;
   double alpha_min_frac, delta, kappa_soc;
   double delta_w_first, delta_w_min, delta_w_max, kappa_w_plus_first, kappa_w_plus, kappa_w_minus;
-  double nlp_scaling_max_gradient, nlp_scaling_min_value, kappa_resto;
-  int max_iter, acceptable_iter, max_soc, mimic_dummy_reg, resto_max_iter, warm_start;
+  double nlp_scaling_max_gradient, nlp_scaling_min_value, kappa_resto, residual_ratio_max;
+  int max_iter, acceptable_iter, max_soc, mimic_dummy_reg, resto_max_iter, warm_start, max_refine, pad_;
 };
 
 enum DmbStatus {
@@ -148,7 +148,8 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define EB_SIGY (EB_GY + NY)
 #define EB_SIGS (EB_SIGY + NY)
 #define EB_RD (EB_SIGS + NNL)
-#define EB_SZ (EB_RD + NNL)
+#define EB_GY2 (EB_RD + NNL)                           // y-part of the refinement right-hand side (NY)
+#define EB_SZ (EB_GY2 + NY)
 // per-node data in shared memory.  Q (NV x NV, v-space) is assembled in parallel (node terms + projected edge
 // Hessians), completed and reduced in place by the sweep: afterwards its leading NXI x NXI block (stride NV) is P.
 #define WN_Q 0                                          // Q / P (NV x NV)
@@ -173,7 +174,8 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define WV_LAMN (WV_LAM + NLAM)
 #define WV_RES (WV_LAMN + NLAM)                          // residuals, same layout as lam
 #define WV_REST (WV_RES + NLAM)
-#define WV_DC (WV_REST + NLAM)                           // row scaling, same layout as lam
+#define WV_LAMR (WV_REST + NLAM)                         // primary multipliers while a refinement solve is running
+#define WV_DC (WV_LAMR + NLAM)                           // row scaling, same layout as lam
 #define WV_S (WV_DC + NLAM)                              // inequality slacks (NEDGE*NNL)
 #define WV_ST (WV_S + NEDGE * NNL)
 #define WV_DS (WV_ST + NEDGE * NNL)
@@ -196,7 +198,7 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #endif
 struct Inst {
   long long* sub;      // optional fine-grained cycle counters (thread 0 only), see SUB_TICK
-  double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *res, *rest, *dc, *s, *st, *ds, *vU;
+  double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *lamr, *res, *rest, *dc, *s, *st, *ds, *vU;
   double *er, *node, *eb;
   const double *p, *lb, *ub;
   double df, relax_fac, relax_max;
@@ -204,7 +206,7 @@ struct Inst {
 DMB_DEV void bind_vectors(Inst& I, double* vec) {
   I.w = vec + WV_W; I.wt = vec + WV_WT; I.dw = vec + WV_DW; I.zL = vec + WV_ZL; I.zU = vec + WV_ZU;
   I.gl = vec + WV_GL; I.go = vec + WV_GO;
-  I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
+  I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.lamr = vec + WV_LAMR; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
   I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU;
 }
 DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + k * DMB_NTVP; }
@@ -1001,7 +1003,8 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
 // forward roll-out (warp 0) then, per edge by its lane group: dy = Yext [dv; 1], new multipliers by a
 // transposed LU solve in the group tile, inequality steps.
 // ---------------------------------------------------------------------------------------------------
-DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, double* tile_base) {
+DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, int refine, double* tile_base) {
+  const int gy_off = refine ? EB_GY2 : EB_GY;
   SUB_START();
   if (c.warp == 0) {
     for (int n = 0; n < NNODE; ++n) {
@@ -1057,11 +1060,11 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
       DMB_COPY_BATCH(NY * NY, c.gl, GSZ, eb[EB_LU + idx], T[(idx / NY) * TILE_LD + idx % NY] = val);
       DMB_COPY_BATCH(NY * NE, c.gl, GSZ, eb[EB_Y + idx], T[(idx / NE) * TILE_LD + NY + idx % NE] = val);
       DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
-      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_GY + idx], T[STG_GY + idx] = val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[gy_off + idx], T[STG_GY + idx] = val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
 #if NNL > 0
       for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
-      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = eb[EB_RD + i]; }
+      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? 0.0 : eb[EB_RD + i]; }
 #endif
       const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];

@@ -1,0 +1,290 @@
+// Iterative refinement of the Newton step (IPOPT: min_refinement_steps / residual_ratio_max, PDFullSpaceSolver).
+//
+// The structured elimination (edge LU + Riccati sweep) is not backward stable like a pivoted LDL^T: with
+// Sigma = z/s ~ 1e12 near the end of badly scaled problems (industrial_poly) the computed step satisfies the
+// linear KKT system only to ~1e-8, which stalls the dual infeasibility just above tol.  Here the residual of the
+// (condensed) KKT system is evaluated with the original sparse data and the step is corrected by re-solving
+// with the existing factors (edge LU, Y, P, K):
+//     rho_d = g_phi + (W + Sigma + delta) dw + J' lam+        rho_p = c + J dw
+//     (ddw, dlam) = S(rho_d, rho_p) ;  dw -= ... (signs as in the primary solve: S solves  K [dw; lam+] = -[g; c]).
+#pragma once
+#include "ipm_core.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// residual of the linear system for the current (dw, ds, lamn).  rd -> I.gl (NWI), rp -> I.rest (NLAM).
+// Uses the per-edge scratch EB_GCON (NQ) for the edge-local part.  Returns max-norms through out[3]:
+// |rho|, |sol|, |rhs|.
+// ---------------------------------------------------------------------------------------------------
+DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, double delta,
+                            double* red, double* out) {
+  double* rd = I.gl; double* rp = I.rest;
+  double nrm_rho = 0.0, nrm_sol = 0.0, nrm_rhs = 0.0;
+  for (int e = c.tid; e < NEDGE; e += c.nthr) {
+    double* eb = I.eb + (size_t)e * EB_SZ;
+    const double* dc = I.dc + LAM_EDGE(e);
+    const double* ln = I.lamn + LAM_EDGE(e);
+    const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
+    const double* dy = I.dw + EDGE_OFF(e);
+    double dq[NQ], hq[NQ];
+#pragma unroll
+    for (int i = 0; i < NVP; ++i) dq[i] = dvp[i];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) dq[NVP + i] = dy[i];
+    gen_hmul(eb + EB_HNZ, dq, hq);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) hq[NVP + i] += (eb[EB_SIGY + i] + delta) * dq[NVP + i] + eb[EB_GY + i];
+    // J_G' lam_G+ and J_G dq (row scaled)
+    double jdq[NY > 0 ? NY : 1];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) jdq[i] = 0.0;
+    for (int k = 0; k < DMB_NNZ_J; ++k) {
+      const int r = DMB_J_ROW[k], cq = DMB_J_COL[k];
+      const double a = dc[r] * eb[EB_JNZ + k];
+      hq[cq] += a * ln[r];
+      jdq[r] += a * dq[cq];
+    }
+#if NNL > 0
+    for (int i = 0; i < NNL; ++i) {
+      double jd = 0.0;
+      for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) jd += eb[EB_DNZ + t] * dq[DMB_D_COL[t]];
+      const double yd = eb[EB_SIGS + i] * jd + eb[EB_RD + i];          // = y_d+ of the condensed system
+      for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) hq[DMB_D_COL[t]] += eb[EB_DNZ + t] * yd;
+      rp[LAM_EDGE(e) + NY + NX + i] = 0.0;                             // eliminated exactly
+    }
+#endif
+    // continuity: + E' lam_C+ on the end-of-interval state, row residual
+    const double* dxc = I.dw + NODE_OFF(DMB_EDGE_CHILD[e]);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      hq[NVP + DMB_XF_SEL[i]] += ln[NY + i];
+      const double r = res[LAM_EDGE(e) + NY + i] + dq[NVP + DMB_XF_SEL[i]] - dxc[i];
+      rp[LAM_EDGE(e) + NY + i] = r;
+      nrm_rho = fmax(nrm_rho, fabs(r));
+    }
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      const double r = res[LAM_EDGE(e) + i] + jdq[i];
+      rp[LAM_EDGE(e) + i] = r;
+      nrm_rho = fmax(nrm_rho, fabs(r));
+      rd[EDGE_OFF(e) + i] = hq[NVP + i];
+      nrm_rho = fmax(nrm_rho, fabs(hq[NVP + i]));
+      nrm_rhs = fmax(nrm_rhs, fmax(fabs(eb[EB_GY + i]), fabs(res[LAM_EDGE(e) + i])));
+      nrm_sol = fmax(nrm_sol, fmax(fabs(dq[NVP + i]), fabs(ln[i])));
+    }
+#pragma unroll
+    for (int i = 0; i < NVP; ++i) eb[EB_GCON + i] = hq[i];
+  }
+  CTA_SYNC();
+  for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
+    const int n = idx / NVP, i = idx - n * NVP;
+    const int k = DMB_NODE_K[n];
+    if (k == NHOR && i >= NX) { rd[idx] = 0.0; continue; }
+    const double* wn = I.node + (size_t)n * WN_NODE;
+    const double lo = I.lb[idx], hi = I.ub[idx], wx = I.w[idx], d = I.dw[idx];
+    const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
+    double sig = delta, g = I.go[idx];
+    if (hl) { const double rs = 1.0 / (wx - lo); sig += I.zL[idx] * rs; g -= mu * rs; if (!hu) g += kappa_d * mu; }
+    if (hu) { const double rs = 1.0 / (hi - wx); sig += I.zU[idx] * rs; g += mu * rs; if (!hl) g -= kappa_d * mu; }
+    double r = g + sig * d;
+    nrm_rhs = fmax(nrm_rhs, fabs(g)); nrm_sol = fmax(nrm_sol, fabs(d));
+    if (k < NHOR)
+      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) r += I.eb[(size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ + EB_GCON + i];
+    const int pe = DMB_NODE_PARENT_EDGE[n];
+    if (i < NX) {
+      if (pe >= 0) {
+        r -= I.lamn[LAM_EDGE(pe) + NY + i];
+        if (k == NHOR) {
+          double hm[NX * NX];
+          gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm);
+          const double wgt = I.df * DMB_EDGE_OMEGA[pe];
+          for (int b = 0; b < NX; ++b) r += wgt * hm[i * NX + b] * I.dw[NODE_OFF(n) + b];
+        }
+      } else r += I.lamn[i];
+    } else if (i < NX + NU) {
+      const int iu = i - NX;
+      // own rterm: rows of u ; children's rterm: rows of their u_prev = this u
+      const double* dup = pe >= 0 ? I.dw + NODE_OFF(DMB_EDGE_PARENT[pe]) + NX : nullptr;
+      for (int b = 0; b < NU; ++b) {
+        r += wn[WN_RH + iu * 2 * NU + b] * I.dw[NODE_OFF(n) + NX + b];
+        if (dup) r += wn[WN_RH + iu * 2 * NU + NU + b] * dup[b];
+      }
+      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+        const int cn = DMB_EDGE_CHILD[DMB_NODE_FIRST_EDGE[n] + j];
+        if (DMB_NODE_K[cn] == NHOR) continue;
+        const double* wc = I.node + (size_t)cn * WN_NODE;
+        for (int b = 0; b < NU; ++b)
+          r += wc[WN_RH + (NU + iu) * 2 * NU + b] * I.dw[NODE_OFF(cn) + NX + b] + wc[WN_RH + (NU + iu) * 2 * NU + NU + b] * I.dw[NODE_OFF(n) + NX + b];
+      }
+    }
+    rd[idx] = r;
+    nrm_rho = fmax(nrm_rho, fabs(r));
+  }
+  for (int i = c.tid; i < NX; i += c.nthr) {
+    const double r = res[i] + I.dw[NODE_OFF(0) + i];
+    rp[i] = r;
+    nrm_rho = fmax(nrm_rho, fabs(r));
+  }
+  out[0] = block_max(c, nrm_rho, red);
+  out[1] = block_max(c, nrm_sol, red);
+  out[2] = block_max(c, nrm_rhs, red);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// right-hand-side dependent part of the edge elimination for a new rhs (rd = I.gl, rp = I.rest), using the stored
+// LU / Y: y0 = -G_y^{-1} rp_G, reduced gradient, Y'y0, b.  One lane group per edge, data staged in the tile.
+// Overwrites ER_GH / ER_YTY0 / ER_B, the y0 column of EB_Y and EB_GY (:= rd_y) — the primary values are no longer
+// needed once the primary step has been recovered (the primary g_y in EB_GY is kept for further residual evaluations).
+// ---------------------------------------------------------------------------------------------------
+DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
+  const double* rd = I.gl; const double* rp = I.rest;
+  double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  double* bv = T + STG_DQ;                      // NY: permuted rhs / solution
+  double* zq = bv + NY;                         // NQ: H (0; y0)
+  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
+    const int e = e0 + c.grp;
+    const bool act = e < NEDGE;
+    double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+    double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
+    if (act) {
+      DMB_COPY_BATCH(NY * NY, c.gl, GSZ, eb[EB_LU + idx], T[(idx / NY) * TILE_LD + idx % NY] = val);
+      DMB_COPY_BATCH(NY * NE, c.gl, GSZ, eb[EB_Y + idx], T[(idx / NE) * TILE_LD + NY + idx % NE] = val);
+      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
+      for (int m = c.gl; m < NY; m += GSZ) bv[m] = rp[LAM_EDGE(e) + (int)eb[EB_PIV + m]];      // P rp_G
+    }
+    WARP_SYNC();
+    // L b' = P rp_G (unit lower), U x = b' (reciprocal diagonal): column sweeps, lanes over rows
+    for (int k = 0; k < NY; ++k) {
+      if (act) { const double bk = bv[k]; for (int r = k + 1 + c.gl; r < NY; r += GSZ) bv[r] -= T[r * TILE_LD + k] * bk; }
+      WARP_SYNC();
+    }
+    for (int k = NY - 1; k >= 0; --k) {
+      double xk = 0.0;
+      if (act) {
+        xk = bv[k] * T[k * TILE_LD + k];
+        for (int r = c.gl; r < k; r += GSZ) bv[r] -= T[r * TILE_LD + k] * xk;
+      }
+      WARP_SYNC();
+      if (act && c.gl == 0) bv[k] = -xk;          // y0 = -x
+      WARP_SYNC();
+    }
+    if (act) {
+      // zq = H_e (0; y0) + Sigma_y y0 ; staged generated product by one lane (straight-line)
+      if (c.gl == 0) {
+        double v[NQ], z[NQ];
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) v[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) v[NVP + i] = bv[i];
+        gen_hmul(T + STG_HNZ, v, z);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) z[NVP + i] += T[STG_SIGY + i] * bv[i];
+#if NNL > 0
+        for (int i = 0; i < NNL; ++i) {
+          double jd = 0.0;
+          for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) if (DMB_D_COL[t] >= NVP) jd += eb[EB_DNZ + t] * bv[DMB_D_COL[t] - NVP];
+          for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) z[DMB_D_COL[t]] += eb[EB_DNZ + t] * eb[EB_SIGS + i] * jd;
+        }
+#endif
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) zq[i] = z[i];
+      }
+    }
+    WARP_SYNC();
+    if (act) {
+      for (int a = c.gl; a < NVP; a += GSZ) {
+        double g = zq[a], yy = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < NY; ++j) {
+          const double yja = T[j * TILE_LD + NY + a];
+          g += yja * (rd[EDGE_OFF(e) + j] + zq[NVP + j]);
+          yy += yja * bv[j];
+        }
+        er[ER_GH + a] = g; er[ER_YTY0 + a] = yy;
+      }
+      for (int i = c.gl; i < NX; i += GSZ) er[ER_B + i] = bv[DMB_XF_SEL[i]] + rp[LAM_EDGE(e) + NY + i];
+      for (int j = c.gl; j < NY; j += GSZ) { eb[EB_Y + j * NE + NVP] = bv[j]; eb[EB_GY2 + j] = rd[EDGE_OFF(e) + j]; }
+    }
+    WARP_SYNC();
+  }
+  CTA_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// vector part of the Riccati sweep for a new right-hand side, re-using Q_xu, Q_uu, P (in place) and K:
+// q0 = rd[node vars] + sum_e (GH_e + delta Y'y0_e) ; q += [A B]'(p_c + P_c b) ; k = -Q_uu^{-1} q_u ; p = q_x + Q_xu k.
+// ---------------------------------------------------------------------------------------------------
+DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double* Qs) {
+  const double* rd = I.gl;
+  for (int idx = c.tid; idx < NNODE * NV; idx += c.nthr) {
+    const int n = idx / NV, a = idx - n * NV;
+    double* wn = I.node + (size_t)n * WN_NODE;
+    const int k = DMB_NODE_K[n];
+    const int ia = a < NX ? a : (a >= NXI ? a - NU : -1);
+    double val = 0.0;
+    if (ia >= 0 && !(k == NHOR && ia >= NX)) {
+      val = rd[NODE_OFF(n) + ia];
+      if (k < NHOR)
+        for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+          const double* er = I.er + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * ER_SZ;
+          val += er[ER_GH + ia] + delta * er[ER_YTY0 + ia];
+        }
+    }
+    wn[WN_QV + a] = val;
+  }
+  CTA_SYNC();
+  if (c.warp == 0) {
+    double* pb = Qs;
+    for (int n = NNODE - 1; n >= 0; --n) {
+      if (DMB_NODE_K[n] == NHOR) continue;
+      double* wn = I.node + (size_t)n * WN_NODE;
+      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
+        const int e = DMB_NODE_FIRST_EDGE[n] + j;
+        const double* er = I.er + (size_t)e * ER_SZ;
+        const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+        for (int r = c.lane; r < NXI; r += DMB_LANES) {
+          double s = wc[WN_QV + r];
+#pragma unroll
+          for (int t = 0; t < NX; ++t) s += P_AT(wc, r, t) * er[ER_B + t];
+          pb[r] = s;
+        }
+        WARP_SYNC();
+        for (int i = c.lane; i < NVP; i += DMB_LANES) {
+          double s = (i >= NX && i < NX + NU) ? pb[i] : 0.0;
+#pragma unroll
+          for (int r = 0; r < NX; ++r) s += er[ER_AB + r * NVP + i] * pb[r];
+          wn[WN_QV + VPOS(i)] += s;
+        }
+        WARP_SYNC();
+      }
+      // k = -Q_uu^{-1} q_u by every lane redundantly (tiny), then p
+      double L[NUT * NUT], kv[NUT];
+#pragma unroll
+      for (int a = 0; a < NUT; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          double s = wn[WN_Q + (NXI + a) * NV + NXI + b];
+#pragma unroll
+          for (int t = 0; t < b; ++t) s -= L[a * NUT + t] * L[b * NUT + t];
+          if (a == b) L[a * NUT + a] = rsqrt(s > 0.0 ? s : 1.0);
+          else L[a * NUT + b] = s * L[b * NUT + b];
+        }
+#pragma unroll
+      for (int a = 0; a < NUT; ++a) kv[a] = -wn[WN_QV + NXI + a];
+#pragma unroll
+      for (int a = 0; a < NUT; ++a) { double s = kv[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * kv[t]; kv[a] = s * L[a * NUT + a]; }
+#pragma unroll
+      for (int a = NUT - 1; a >= 0; --a) { double s = kv[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * kv[t]; kv[a] = s * L[a * NUT + a]; }
+      WARP_SYNC();
+      for (int a = c.lane; a < NUT; a += DMB_LANES) wn[WN_KV + a] = kv[a];
+      for (int a = c.lane; a < NXI; a += DMB_LANES) {
+        double s = wn[WN_QV + a];
+#pragma unroll
+        for (int t = 0; t < NUT; ++t) s += wn[WN_Q + a * NV + NXI + t] * kv[t];
+        wn[WN_QV + a] = s;
+      }
+      WARP_SYNC();
+    }
+  }
+  CTA_SYNC();
+}

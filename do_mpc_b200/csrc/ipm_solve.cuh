@@ -2,6 +2,7 @@
 // Algorithm and constants: Waechter & Biegler (2006), IPOPT defaults — identical to oracle/ipm.py.
 #pragma once
 #include "ipm_core.cuh"
+#include "ipm_refine.cuh"
 
 #ifdef DMB_HOSTSIM
 #include <stdio.h>
@@ -158,7 +159,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   eval_derivatives(c, I);                       // lam = 0: objective gradient and Jacobian at the pushed point
   factor_edges(c, I, I.rest, 0.0, 0.0, 1, tile, &S->fail);
   riccati_backward(c, I, 0.0, 0.0, 0.0, 1, Qs, &S->flag);
-  forward_recover(c, I, I.rest, 0.0, 1, tile);
+  forward_recover(c, I, I.rest, 0.0, 1, 0, tile);
   {
     double m = 0.0;
     for (int i = c.tid; i < NLAM; i += c.nthr) m = fmax(m, fabs(I.lamn[i]));
@@ -234,7 +235,28 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     if (step_fail) { status = DMB_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
     DMB_TICK(3);
-    forward_recover(c, I, I.res, delta_w, 0, tile);
+    forward_recover(c, I, I.res, delta_w, 0, 0, tile);
+    // ---- iterative refinement of the step (IPOPT: residual_ratio_max 1e-10) ------------------------------------------
+    for (int ref_it = 0; ref_it < o.max_refine; ++ref_it) {
+      double nr[3];
+      kkt_residual(c, I, I.res, mu, o.kappa_d, delta_w, red, nr);
+      const double ratio = nr[0] / (fmin(nr[1], 1e6 * nr[2]) + nr[2] + 1e-300);
+#ifdef DMB_HOSTSIM
+      if (dmb_hostsim_verbose) printf("     refine %d: |rho|=%.3e |sol|=%.3e |rhs|=%.3e ratio=%.3e\n", ref_it, nr[0], nr[1], nr[2], ratio);
+#endif
+      if (!(ratio > o.residual_ratio_max)) break;
+      for (int i = c.tid; i < NWI; i += c.nthr) I.wt[i] = I.dw[i];
+      for (int i = c.tid; i < NLAM; i += c.nthr) I.lamr[i] = I.lamn[i];
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.ds[i];
+      CTA_SYNC();
+      resolve_edges(c, I, tile);
+      riccati_vector(c, I, delta_w, Qs);
+      forward_recover(c, I, I.rest, delta_w, 0, 1, tile);
+      for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];
+      for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] += I.lamr[i];
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.ds[i] += I.st[i];
+      CTA_SYNC();
+    }
     DMB_TICK(4);
 
     // ---- step sizes, directional derivative (I.go = objective gradient, scaled by df) ------------------------------

@@ -9,8 +9,8 @@ _D = ["tol", "dual_inf_tol", "constr_viol_tol", "compl_inf_tol",
       "alpha_red_factor", "eta_phi", "theta_max_fact", "theta_min_fact", "s_phi", "s_theta", "gamma_phi", "gamma_theta",
       "alpha_min_frac", "delta", "kappa_soc",
       "delta_w_first", "delta_w_min", "delta_w_max", "kappa_w_plus_first", "kappa_w_plus", "kappa_w_minus",
-      "nlp_scaling_max_gradient", "nlp_scaling_min_value", "kappa_resto"]
-_I = ["max_iter", "acceptable_iter", "max_soc", "mimic_dummy_reg", "resto_max_iter", "warm_start"]
+      "nlp_scaling_max_gradient", "nlp_scaling_min_value", "kappa_resto", "residual_ratio_max"]
+_I = ["max_iter", "acceptable_iter", "max_soc", "mimic_dummy_reg", "resto_max_iter", "warm_start", "max_refine", "pad_"]
 
 
 class DmbOptions(ctypes.Structure):

@@ -68,7 +68,7 @@ def test_make_step_loop_like_reference_regression_test():
     assert pred.shape == (1, 21, 1)
 
 
-def test_industrial_poly_solution_within_tolerance_on_gpu():
+def test_industrial_poly_matches_reference_on_gpu():
     make, _ = EXAMPLES["industrial_poly"]
     mpc = make(setup=True)
     r = mpc.recipe
@@ -76,5 +76,6 @@ def test_industrial_poly_solution_within_tolerance_on_gpu():
     mpc.S.set_options(max_iter=300)
     P, x0s, u0s, z0s = cold_start_inputs(r, g)
     out = mpc.S.solve_batch(P, x0s, u0s, z0s, lbx=mpc._lb_opt_x.full().ravel(), ubx=mpc._ub_opt_x.full().ravel(), return_full=True)
+    assert out["status"][0] == 0
     assert np.abs(out["u0_scaled"][0] - g["u"][0] / r.u_scaling).max() < TOL
     assert np.abs(out["g"][0]).max() < 1e-7
