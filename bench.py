@@ -285,12 +285,14 @@ def main():
                        "success_rate": float(ok.mean()), "mean_iters": float(iters.mean()), "max_iters": int(iters.max())},
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (r.n_p + r.n_x + r.n_u) * 8),
-                    "d2h_bytes_per_step": int(B * (r.n_u * 8 + 8 + 4 + 4 + 4 * 8))},
+                    "d2h_bytes_per_step": int(B * (r.n_u * 8 + 8 + 4 + 4 + out["stats"].shape[1] * 8))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms, "phase_share_of_cta_cycles": phases,
-                         "subphase_share": {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
-                             ["f_assemble", "f_lu", "f_backsub", "f_mn", "f_reduce", "ric_sweep", "fwd_sweep", "-"], sub)},
+                         "traffic": traffic, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms,
+                         **({"phase_share_of_cta_cycles": phases,
+                             "subphase_share": {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
+                                 ["f_assemble", "f_lu", "f_backsub", "f_mn", "f_reduce", "ric_sweep", "fwd_sweep", "-"], sub)}}
+                            if ph.sum() > 0 else {}),
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "algorithmic bytes = A_B(23.3 KB)/IPM iteration x total iterations; iterate state lives in shared memory, "
                                  "so DRAM traffic is far below this and the kernel is latency/issue bound (DESIGN.md §Roofline)"},

@@ -58,7 +58,7 @@ def launch_config(r: Recipe, src: str):
     """(threads per CTA, reduced blocks + node data in shared memory?, iterate vectors in shared memory?, CTAs/SM the
     register budget is compiled for).  227 KB of shared memory per SM on sm_100; measured on B200 (cfg #2): 3 CTAs/SM
     with the iterate vectors in the L1/L2-backed slot beat 2 CTAs/SM with everything on chip (132.6k vs 110.6k solves/s)."""
-    threads = 128
+    threads = int(os.environ.get("DMB_FORCE_THREADS", "128"))     # override: tuning experiments only
     fixed, ern, vec = _sizes(r, src, threads)
     if 8 * fixed > 150 * 1024:
         threads = 64
