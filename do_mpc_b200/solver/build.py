@@ -90,7 +90,7 @@ def build_library(r: Recipe, verbose: bool = False) -> Path:
     (d / "problem_gen.h").write_text(src)
     cmd = [NVCC, *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
            f"-DDMB_THREADS={threads}", f"-DDMB_ERN_SMEM={ern_smem}", f"-DDMB_VEC_SMEM={vec_smem}", f"-DDMB_MIN_CTAS={min_ctas}", *extra, f"-I{d}", f"-I{CSRC}", f"-I{INCLUDE}",
-           str(CSRC / "dmb_api.cu"), "-o", str(lib) + ".tmp"]
+           str(CSRC / "dmb_api.cu"), "-o", str(lib) + f".tmp{os.getpid()}"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -98,6 +98,6 @@ def build_library(r: Recipe, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed for the generated problem library:\n" + " ".join(cmd) + "\n" + res.stderr[-6000:])
     if verbose:
         print(res.stderr)
-    os.replace(str(lib) + ".tmp", lib)
+    os.replace(str(lib) + f".tmp{os.getpid()}", lib)        # atomic: concurrent ranks may build the same library
     (d / "build_cmd.txt").write_text(" ".join(cmd) + "\n")
     return lib
