@@ -2,7 +2,7 @@
 (reference do_mpc/__init__.py:103-128).  Subsystems outside the hot path (simulator, estimators, graphics, ...)
 are not provided; accessing them raises with a clear message."""
 import do_mpc_b200 as _b
-from do_mpc_b200 import model, controller, data  # noqa: F401
+from do_mpc_b200 import model, controller, data, simulator, estimator  # noqa: F401
 
 __version__ = _b.__version__
 
@@ -13,5 +13,5 @@ class _Missing:
         raise NotImplementedError(f"do_mpc.{self._n}.{item} is outside the scope of do_mpc_b200 (controller hot path only)")
 
 
-simulator = _Missing("simulator"); estimator = _Missing("estimator"); graphics = _Missing("graphics")
+graphics = _Missing("graphics")
 sampling = _Missing("sampling"); approximateMPC = _Missing("approximateMPC"); differentiator = _Missing("differentiator")

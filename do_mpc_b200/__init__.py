@@ -10,6 +10,8 @@ from . import model as _model_mod
 from . import data
 from . import controller as _controller_mod
 from . import casadi_api
+from . import simulator as _sim_mod
+from . import estimator as _est_mod
 
 __version__ = "0.1.0"
 
@@ -21,3 +23,5 @@ class _NS:
 
 model = _NS(Model=_model_mod.Model)
 controller = _NS(MPC=_controller_mod.MPC, MPCSettings=_controller_mod.MPCSettings)
+simulator = _NS(Simulator=_sim_mod.Simulator)
+estimator = _NS(StateFeedback=_est_mod.StateFeedback, Estimator=_est_mod.Estimator)

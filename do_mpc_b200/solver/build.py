@@ -101,3 +101,28 @@ def build_library(r: Recipe, verbose: bool = False) -> Path:
     os.replace(str(lib) + f".tmp{os.getpid()}", lib)        # atomic: concurrent ranks may build the same library
     (d / "build_cmd.txt").write_text(" ".join(cmd) + "\n")
     return lib
+
+
+def build_sim_library(model, deg: int = 3) -> Path:
+    """Plant-simulator library for a model (csrc/sim_api.cu + generated sim_gen.h), cached like the solver libraries."""
+    from .sim_codegen import generate_sim
+    src = generate_sim(model, deg)
+    h = hashlib.sha256(src.encode())
+    for f in ("sim_core.cuh", "sim_api.cu"):
+        h.update((CSRC / f).read_bytes())
+    h.update((INCLUDE / "dompc_b200_sim.h").read_bytes())
+    key = h.hexdigest()[:16]
+    d = CACHE / f"sim_{key}"
+    lib = d / f"libdms_{key}.so"
+    if lib.exists():
+        return lib
+    d.mkdir(parents=True, exist_ok=True)
+    (d / "sim_gen.h").write_text(src)
+    tmp = str(lib) + f".tmp{os.getpid()}"
+    cmd = [NVCC, *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", f"-I{d}", f"-I{CSRC}",
+           f"-I{INCLUDE}", str(CSRC / "sim_api.cu"), "-o", tmp]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for the generated simulator library:\n" + " ".join(cmd) + "\n" + res.stderr[-6000:])
+    os.replace(tmp, lib)
+    return lib

@@ -1,0 +1,42 @@
+"""Closed loop MPC -> Simulator -> StateFeedback on the GPU, exactly as the reference's regression tests run it
+(testing/test_CSTR.py:113-116 etc.): 5 steps, compared with the golden closed-loop trajectories `_x`, `_u`."""
+import numpy as np
+import pytest
+
+import do_mpc_b200 as do_mpc
+from examples_common import EXAMPLES, golden
+
+pytestmark = pytest.mark.gpu
+
+PLANT = {"CSTR": dict(alpha=1.0, beta=1.0), "batch_reactor": dict(Y_x=0.5, S_in=200.0),
+         "industrial_poly": dict(delH_R=950.0, k_0=7.0), "oscillatingMasses": {}}
+
+
+@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "industrial_poly"])
+def test_five_closed_loop_steps_match_reference_goldens(name):
+    make, _ = EXAMPLES[name]
+    mpc = make(setup=True)
+    mpc.S.set_options(max_iter=500)
+    model = mpc.model
+    g = golden(name)
+    sim = do_mpc.simulator.Simulator(model)
+    sim.set_param(t_step=mpc.settings.t_step)
+    if model.n_p:
+        p_num = sim.get_p_template()
+        for k, v in PLANT[name].items():
+            p_num[k] = v
+        sim.set_p_fun(lambda t: p_num)
+    sim.setup()
+    est = do_mpc.estimator.StateFeedback(model)
+    x0 = g["x"][0].reshape(-1, 1)
+    mpc.x0 = x0; sim.x0 = x0; est.x0 = x0
+    mpc.set_initial_guess()
+    for k in range(5):
+        u0 = mpc.make_step(x0)
+        y = sim.make_step(u0)
+        x0 = est.make_step(y)
+    sx, su = mpc.recipe.x_scaling, mpc.recipe.u_scaling
+    assert np.abs((mpc.data["_x"] - g["x"]) / sx).max() < 1e-5 * max(1.0, np.abs(g["x"] / sx).max())
+    assert np.abs((mpc.data["_u"] - g["u"]) / su).max() < 1e-5 * max(1.0, np.abs(g["u"] / su).max())
+    assert np.abs(sim.data["_x"] - g["x"]).max() / (1 + np.abs(g["x"]).max()) < 1e-5
+    assert mpc.data["success"].min() == 1.0
