@@ -10,6 +10,7 @@ from . import model as _model_mod
 from . import data
 from . import controller as _controller_mod
 from . import casadi_api
+from . import sampling
 from . import simulator as _sim_mod
 from . import estimator as _est_mod
 

@@ -100,3 +100,18 @@ def test_device_resident_api_matches_host_api(mpc, dataset):
     torch.cuda.synchronize()
     assert np.array_equal(dev["status"].cpu().numpy(), host["status"])
     assert np.array_equal(dev["u0_scaled"].cpu().numpy(), host["u0_scaled"])
+
+
+def test_batched_sampler_reproduces_reference_dataset_table(mpc, dataset):
+    """do_mpc_b200.sampling: the reference's serial AMPCSampler loop as one batched solve, same table columns."""
+    from do_mpc_b200.sampling import sample_open_loop, sampling_plan_box
+    plan = [{"x0": dataset["x0"][i].reshape(-1, 1), "u_prev": dataset["u_prev"][i].reshape(-1, 1), "id": f"{i:03d}"} for i in range(200)]
+    df = sample_open_loop(mpc, plan)
+    assert list(df.columns) == ["x0", "u_prev", "id", "u0", "status", "t_make_step", "t_wall", "iter_count"]
+    assert np.array_equal(df["status"].to_numpy(), dataset["success"][:200].astype(bool))
+    ok = df["status"].to_numpy()
+    u0 = np.array([df.iloc[i]["u0"].ravel() for i in np.where(ok)[0]])
+    assert np.abs(u0 - dataset["u0"][:200][ok]).max() / 2000 < 1e-5
+    assert np.abs(df["iter_count"].to_numpy()[ok] - dataset["iter_count"][:200][ok]).max() <= 1
+    p2 = sampling_plan_box(mpc, 16, seed=42)
+    assert len(p2) == 16 and p2[0]["x0"].shape == (4, 1) and np.all(p2[3]["u_prev"].ravel() <= [100, 0])
