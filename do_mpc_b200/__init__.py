@@ -11,6 +11,7 @@ from . import data
 from . import controller as _controller_mod
 from . import casadi_api
 from . import sampling
+from . import differentiator as _diff_mod
 from . import simulator as _sim_mod
 from . import estimator as _est_mod
 
@@ -26,3 +27,5 @@ model = _NS(Model=_model_mod.Model)
 controller = _NS(MPC=_controller_mod.MPC, MPCSettings=_controller_mod.MPCSettings)
 simulator = _NS(Simulator=_sim_mod.Simulator)
 estimator = _NS(StateFeedback=_est_mod.StateFeedback, Estimator=_est_mod.Estimator)
+differentiator = _NS(DoMPCDifferentiator=_diff_mod.DoMPCDifferentiator, NLPDifferentiatorSettings=_diff_mod.NLPDifferentiatorSettings,
+                     NLPDifferentiatorStatus=_diff_mod.NLPDifferentiatorStatus, indexf=_diff_mod.indexf)

@@ -480,4 +480,5 @@ class MPC:
                                  None if Zs is None else Zs / r.z_scaling,
                                  self._lb_opt_x.full().ravel(), self._ub_opt_x.full().ravel(), return_full=return_full)
         out["u0"] = out["u0_scaled"] * r.u_scaling
+        out["p"] = P_
         return out

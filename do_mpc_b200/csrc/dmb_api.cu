@@ -6,6 +6,7 @@
 #include <new>
 
 #include "ipm_solve.cuh"
+#include "ipm_sens.cuh"
 #include "dmb_host_util.h"
 #include "dompc_b200.h"
 
@@ -95,6 +96,62 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
   }
 }
 
+// ---- parametric sensitivities of solved instances (see ipm_sens.cuh) --------------------------------------------
+struct SensArgs {
+  int B, mode, ncols;
+  const double *x, *lam_g, *p, *lbI, *ubI, *lb0, *ub0;
+  const int *cols, *status;
+  int rule;
+  double *dx, *dlam, *ws;
+  int *sstat, *counter;
+  double tol, big, ratio_max;
+  int max_refine;
+  double relax_fac, relax_max;
+};
+
+__global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_sens_kernel(const SensArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  DmbShared* S = reinterpret_cast<DmbShared*>(sm + SM_DOUBLES);
+  __shared__ int cur;
+  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
+        (int)(threadIdx.x % GSZ), (int)(threadIdx.x / GSZ), (int)(blockDim.x / GSZ)};
+  double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
+  Inst I;
+  bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot + SLOT_VEC);
+  I.er = DMB_ERN_SMEM ? sm + SM_ER : slot + SLOT_ERN;
+  I.node = I.er + (size_t)NEDGE * ER_SZ;
+  I.eb = slot + SLOT_EB;
+  I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
+  I.relax_fac = a.relax_fac; I.relax_max = a.relax_max;
+  const size_t nrow = a.mode == 1 ? NU : DMB_NW;
+  while (true) {
+    if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int b = cur;
+    __syncthreads();
+    if (b >= a.B) break;
+    I.p = a.p + (size_t)b * DMB_NP;
+    int st;
+    if (a.status && a.status[b] != DMB_SOLVE_SUCCEEDED && a.status[b] != DMB_SOLVED_TO_ACCEPTABLE_LEVEL) st = DMB_SENS_SKIPPED;
+    else st = sens_factor(c, I, a.x + (size_t)b * DMB_NW, a.lam_g + (size_t)b * DMB_NG, a.rule ? a.lbI : a.lb0, a.rule ? a.ubI : a.ub0, a.rule, a.tol, a.big, sm + SM_TILE, sm + SM_QS, S);
+    for (int jc = 0; jc < a.ncols; ++jc) {
+      double* dx = a.dx + ((size_t)b * a.ncols + jc) * nrow;
+      double* dl = (a.dlam && a.mode != 1) ? a.dlam + ((size_t)b * a.ncols + jc) * (DMB_NG + DMB_NW) : nullptr;
+      if (st >= DMB_SENS_FAILED) {
+        for (int i = c.tid; i < (int)nrow; i += c.nthr) dx[i] = nan("");
+        if (dl) for (int i = c.tid; i < DMB_NG + DMB_NW; i += c.nthr) dl[i] = nan("");
+        continue;
+      }
+      sens_rhs(c, I, a.cols ? a.cols[jc] : jc);
+      sens_solve(c, I, a.max_refine, a.ratio_max, sm + SM_TILE, sm + SM_QS, S);
+      sens_store(c, I, a.mode, dx, dl);
+    }
+    if (threadIdx.x == 0 && a.sstat) a.sstat[b] = st;
+    __syncthreads();
+  }
+}
+
 // broadcast-free fill of x for the cold-start path when the caller wants the full primal vector:
 // unused reference variables keep the broadcast initial guess (reference _mpc.py:969-971)
 __global__ void dmb_fill_guess_kernel(int B, const double* x0s, const double* u0s, const double* z0s, double* x) {
@@ -134,8 +191,10 @@ __global__ void dmb_aux_kernel(int B, const double* x, const double* p, double* 
 struct dmb_solver {
   int device = 0, n_sm = 0, grid_max = 0, have_bounds = 0;
   DmbOptions opts;
-  double *d_lbI = nullptr, *d_ubI = nullptr, *d_ws = nullptr;
+  double *d_lbI = nullptr, *d_ubI = nullptr, *d_lb0 = nullptr, *d_ub0 = nullptr, *d_ws = nullptr;
   int* d_counter = nullptr;
+  int* d_cols = nullptr; int cols_cap = 0;
+  double sens_tol = 1e-6, sens_big = 1e10; int sens_rule = 0;
   size_t ws_slots = 0;
   // staging for the host entry point
   double* d_stage = nullptr; size_t stage_doubles = 0;
@@ -171,10 +230,12 @@ dmb_solver* dmb_create(int device) {
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return nullptr; }
   s->n_sm = prop.multiProcessorCount;
   if (cudaFuncSetAttribute(dmb_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES) != cudaSuccess) { delete s; return nullptr; }
+  if (cudaFuncSetAttribute(dmb_sens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES) != cudaSuccess) { delete s; return nullptr; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmb_solve_kernel, DMB_THREADS, SM_BYTES) != cudaSuccess || per_sm < 1) { delete s; return nullptr; }
   s->grid_max = per_sm * s->n_sm;
   bool ok = cudaMalloc(&s->d_lbI, sizeof(double) * NWI) == cudaSuccess && cudaMalloc(&s->d_ubI, sizeof(double) * NWI) == cudaSuccess &&
+            cudaMalloc(&s->d_lb0, sizeof(double) * NWI) == cudaSuccess && cudaMalloc(&s->d_ub0, sizeof(double) * NWI) == cudaSuccess &&
             cudaMalloc(&s->d_counter, sizeof(int)) == cudaSuccess &&
             cudaMalloc(&s->d_ws, sizeof(double) * (size_t)SLOT_DOUBLES * s->grid_max) == cudaSuccess &&
             cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
@@ -186,7 +247,7 @@ dmb_solver* dmb_create(int device) {
 void dmb_destroy(dmb_solver* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->d_lbI); cudaFree(s->d_ubI); cudaFree(s->d_counter); cudaFree(s->d_ws); cudaFree(s->d_stage);
+  cudaFree(s->d_lbI); cudaFree(s->d_ubI); cudaFree(s->d_lb0); cudaFree(s->d_ub0); cudaFree(s->d_counter); cudaFree(s->d_ws); cudaFree(s->d_stage); cudaFree(s->d_cols);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -209,6 +270,10 @@ int dmb_set_bounds(dmb_solver* s, const double* lbx, const double* ubx) {
   dmb_internal_bounds(lbx, ubx, &s->opts, lbI, ubI);
   CK(cudaMemcpy(s->d_lbI, lbI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(s->d_ubI, ubI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
+  DmbOptions o0 = s->opts; o0.bound_relax_factor = 0.0;          // the user's bounds, for the reference's active-set test
+  dmb_internal_bounds(lbx, ubx, &o0, lbI, ubI);
+  CK(cudaMemcpy(s->d_lb0, lbI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_ub0, ubI, sizeof(double) * NWI, cudaMemcpyHostToDevice));
   s->have_bounds = 1;
   return DMB_E_OK;
 }
@@ -304,6 +369,71 @@ int dmb_aux_host(dmb_solver* s, int B, const double* x, const double* p, double*
   CK(cudaGetLastError());
   s->n_launches++;
   CK(cudaMemcpy(aux, d + nB * DMB_NW + nB * DMB_NP, nB * DMB_NHOR * DMB_NSCEN * DMB_NAUX * sizeof(double), cudaMemcpyDeviceToHost));
+  return DMB_E_OK;
+}
+
+int dmb_set_sens_options(dmb_solver* s, double active_set_tol, double active_weight, int relaxed_bounds_rule) {
+  if (!s || !(active_set_tol >= 0.0) || !(active_weight > 0.0)) return DMB_E_ARG;
+  s->sens_tol = active_set_tol; s->sens_big = active_weight; s->sens_rule = relaxed_bounds_rule ? 1 : 0;
+  return DMB_E_OK;
+}
+
+int dmb_sens_device(dmb_solver* s, int B, const double* d_x, const double* d_lam_g, const double* d_p, const int* d_status,
+                    int mode, const int* cols, int ncols, double* d_dx, double* d_dlam, int* d_sens_status, void* stream_) {
+  if (!s) return DMB_E_ARG;
+  if (B <= 0 || !d_x || !d_lam_g || !d_p || !d_dx || (mode != DMB_SENS_FULL && mode != DMB_SENS_U0) || ncols < 0 ||
+      (!cols && ncols != 0 && ncols != DMB_NP)) { s->err = "invalid argument"; return DMB_E_ARG; }
+  if (!s->have_bounds) { s->err = "dmb_set_bounds must be called before dmb_sens_*"; return DMB_E_STATE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(cudaSetDevice(s->device));
+  if (!cols) ncols = DMB_NP;
+  if (cols) {
+    for (int i = 0; i < ncols; ++i) if (cols[i] < 0 || cols[i] >= DMB_NP) { s->err = "parameter column out of range"; return DMB_E_ARG; }
+    if (ncols > s->cols_cap) { cudaFree(s->d_cols); s->d_cols = nullptr; s->cols_cap = 0; CK(cudaMalloc(&s->d_cols, sizeof(int) * ncols)); s->cols_cap = ncols; }
+    CK(cudaMemcpyAsync(s->d_cols, cols, sizeof(int) * ncols, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), st));
+  SensArgs a;
+  a.B = B; a.mode = mode; a.ncols = ncols; a.x = d_x; a.lam_g = d_lam_g; a.p = d_p; a.lbI = s->d_lbI; a.ubI = s->d_ubI;
+  a.lb0 = s->d_lb0; a.ub0 = s->d_ub0; a.rule = s->sens_rule;
+  a.cols = cols ? s->d_cols : nullptr; a.status = d_status; a.dx = d_dx; a.dlam = d_dlam; a.ws = s->d_ws; a.sstat = d_sens_status;
+  a.counter = s->d_counter; a.tol = s->sens_tol; a.big = s->sens_big; a.ratio_max = s->opts.residual_ratio_max;
+  a.max_refine = s->opts.max_refine; a.relax_fac = s->opts.bound_relax_factor; a.relax_max = s->opts.constr_viol_tol;
+  const int grid = B < s->grid_max ? B : s->grid_max;
+  CK(cudaEventRecord(s->ev0, st));
+  dmb_sens_kernel<<<grid, DMB_THREADS, SM_BYTES, st>>>(a);
+  CK(cudaEventRecord(s->ev1, st));
+  CK(cudaGetLastError());
+  s->last_grid = grid; s->n_launches++;
+  return DMB_E_OK;
+}
+
+int dmb_sens_host(dmb_solver* s, int B, const double* x, const double* lam_g, const double* p, const int* status, int mode,
+                  const int* cols, int ncols, double* dx, double* dlam, int* sens_status) {
+  if (!s) return DMB_E_ARG;
+  if (B <= 0 || !x || !lam_g || !p || !dx) { s->err = "invalid argument"; return DMB_E_ARG; }
+  CK(cudaSetDevice(s->device));
+  const size_t nB = (size_t)B, nc = cols ? (size_t)ncols : (size_t)DMB_NP, nrow = mode == DMB_SENS_U0 ? NU : DMB_NW;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 1) & ~(size_t)1; return o; };
+  const size_t o_x = take(nB * DMB_NW), o_l = take(nB * DMB_NG), o_p = take(nB * DMB_NP), o_dx = take(nB * nc * nrow),
+               o_dl = take((dlam && mode != DMB_SENS_U0) ? nB * nc * (DMB_NG + DMB_NW) : 0), o_st = take(status ? nB : 0), o_ss = take(nB);
+  int rc = ensure_stage(s, off);
+  if (rc) return rc;
+  double* d = s->d_stage;
+  CK(cudaMemcpyAsync(d + o_x, x, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d + o_l, lam_g, nB * DMB_NG * sizeof(double), cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(d + o_p, p, nB * DMB_NP * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (status) CK(cudaMemcpyAsync(d + o_st, status, nB * sizeof(int), cudaMemcpyHostToDevice, 0));
+  const bool want_dl = dlam && mode != DMB_SENS_U0;
+  rc = dmb_sens_device(s, B, d + o_x, d + o_l, d + o_p, status ? (const int*)(d + o_st) : nullptr, mode, cols, ncols, d + o_dx,
+                       want_dl ? d + o_dl : nullptr, (int*)(d + o_ss), nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(dx, d + o_dx, nB * nc * nrow * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (want_dl) CK(cudaMemcpyAsync(dlam, d + o_dl, nB * nc * (DMB_NG + DMB_NW) * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (sens_status) CK(cudaMemcpyAsync(sens_status, d + o_ss, nB * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
   return DMB_E_OK;
 }
 

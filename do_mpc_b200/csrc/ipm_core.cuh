@@ -851,7 +851,44 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 //        W = P_c [A B]_aug , Q += [A B]_aug' W , Cholesky of Q_uu , K = -Q_uu^{-1} Q_u. , P = Q_xx + Q_xu K (in place).
 // *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
-DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
+// unpivoted L D L' of the control block (row stride NV): strict lower part of L (unit diagonal), diagonal = 1 / D.
+// returns bit 0: zero / non-finite pivot (replaced by 1), bit 1: negative pivot.
+DMB_DEV int quu_ldl(const double* Quu, double* L) {
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < NUT; ++j) {
+    double d = Quu[j * NV + j];
+#pragma unroll
+    for (int t = 0; t < j; ++t) d -= L[j * NUT + t] * L[j * NUT + t] / L[t * NUT + t];
+    if (!(fabs(d) > 1e-300) || !(fabs(d) < 1e300)) { bad |= 1; d = 1.0; }
+    if (d < 0.0) bad |= 2;
+    const double dinv = 1.0 / d;
+    L[j * NUT + j] = dinv;
+#pragma unroll
+    for (int i = j + 1; i < NUT; ++i) {
+      double s = Quu[i * NV + j];
+#pragma unroll
+      for (int t = 0; t < j; ++t) s -= L[i * NUT + t] * L[j * NUT + t] / L[t * NUT + t];
+      L[i * NUT + j] = s * dinv;
+    }
+  }
+  return bad;
+}
+DMB_DEV void quu_ldl_solve(const double* L, double* rhs) {
+#pragma unroll
+  for (int a = 0; a < NUT; ++a) { double s = rhs[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * rhs[t]; rhs[a] = s; }
+#pragma unroll
+  for (int a = 0; a < NUT; ++a) rhs[a] *= L[a * NUT + a];
+#pragma unroll
+  for (int a = NUT - 1; a >= 0; --a) { double s = rhs[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * rhs[t]; rhs[a] = s; }
+}
+
+// LDL = false: Cholesky of every control block, *flag = 1 unless all are positive definite (inertia test of the IPM).
+// LDL = true : unpivoted L D L' instead, valid for indefinite blocks (sensitivity solve, ipm_sens.cuh: the linear system
+//              only has to be regular); *flag bit 0 = singular block, bit 1 = some D < 0 (reduced Hessian indefinite).
+//              The "L" returned through the in-register layout then has unit diagonal and carries 1/D on the diagonal.
+template <bool LDL>
+DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
   CTA_SYNC();                       // every thread has consumed the flag of a previous call before it is reset
   if (c.tid == 0) *flag = 0;
   // ---- (1) node matrices ------------------------------------------------------------------------------------------
@@ -953,6 +990,8 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
       {
         double L[NUT * NUT];              // unit-free Cholesky factor; the diagonal stores 1 / L_aa
         int bad = 0;
+        if (LDL) bad = quu_ldl(wn + WN_Q + NXI * NV + NXI, L);
+        else {
 #pragma unroll
         for (int a = 0; a < NUT; ++a)
 #pragma unroll
@@ -963,15 +1002,19 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
             if (a == b) { if (!(s > 0.0)) { bad = 1; s = 1.0; } L[a * NUT + a] = rsqrt(s); }
             else L[a * NUT + b] = s * L[b * NUT + b];
           }
-        if (bad && c.lane == 0) *flag = 1;
+        }
+        if (bad && c.lane == 0) *flag |= bad;
         for (int col = c.lane; col <= NXI; col += DMB_LANES) {
           double rhs[NUT];
 #pragma unroll
           for (int a = 0; a < NUT; ++a) rhs[a] = col < NXI ? -wn[WN_Q + (NXI + a) * NV + col] : -wn[WN_QV + NXI + a];
+          if (LDL) quu_ldl_solve(L, rhs);
+          else {
 #pragma unroll
           for (int a = 0; a < NUT; ++a) { double s = rhs[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * rhs[t]; rhs[a] = s * L[a * NUT + a]; }
 #pragma unroll
           for (int a = NUT - 1; a >= 0; --a) { double s = rhs[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * rhs[t]; rhs[a] = s * L[a * NUT + a]; }
+          }
 #pragma unroll
           for (int a = 0; a < NUT; ++a) { if (col < NXI) wn[WN_K + a * NXI + col] = rhs[a]; else wn[WN_KV + a] = rhs[a]; }
         }
@@ -997,6 +1040,10 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
     SUB_TICK(I, 5);
   }
   CTA_SYNC();
+}
+
+DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
+  riccati_backward_t<false>(c, I, mu, kappa_d, delta, ls_mode, Qs, flag);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -214,7 +214,8 @@ DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
 // vector part of the Riccati sweep for a new right-hand side, re-using Q_xu, Q_uu, P (in place) and K:
 // q0 = rd[node vars] + sum_e (GH_e + delta Y'y0_e) ; q += [A B]'(p_c + P_c b) ; k = -Q_uu^{-1} q_u ; p = q_x + Q_xu k.
 // ---------------------------------------------------------------------------------------------------
-DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double* Qs) {
+template <bool LDL>
+DMB_PHASE void riccati_vector_t(const Ctx& c, const Inst& I, double delta, double* Qs) {
   const double* rd = I.gl;
   for (int idx = c.tid; idx < NNODE * NV; idx += c.nthr) {
     const int n = idx / NV, a = idx - n * NV;
@@ -259,6 +260,8 @@ DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double*
       }
       // k = -Q_uu^{-1} q_u by every lane redundantly (tiny), then p
       double L[NUT * NUT], kv[NUT];
+      if (LDL) quu_ldl(wn + WN_Q + NXI * NV + NXI, L);
+      else {
 #pragma unroll
       for (int a = 0; a < NUT; ++a)
 #pragma unroll
@@ -269,12 +272,16 @@ DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double*
           if (a == b) L[a * NUT + a] = rsqrt(s > 0.0 ? s : 1.0);
           else L[a * NUT + b] = s * L[b * NUT + b];
         }
+      }
 #pragma unroll
       for (int a = 0; a < NUT; ++a) kv[a] = -wn[WN_QV + NXI + a];
+      if (LDL) quu_ldl_solve(L, kv);
+      else {
 #pragma unroll
       for (int a = 0; a < NUT; ++a) { double s = kv[a]; for (int t = 0; t < a; ++t) s -= L[a * NUT + t] * kv[t]; kv[a] = s * L[a * NUT + a]; }
 #pragma unroll
       for (int a = NUT - 1; a >= 0; --a) { double s = kv[a]; for (int t = a + 1; t < NUT; ++t) s -= L[t * NUT + a] * kv[t]; kv[a] = s * L[a * NUT + a]; }
+      }
       WARP_SYNC();
       for (int a = c.lane; a < NUT; a += DMB_LANES) wn[WN_KV + a] = kv[a];
       for (int a = c.lane; a < NXI; a += DMB_LANES) {
@@ -288,3 +295,4 @@ DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double*
   }
   CTA_SYNC();
 }
+DMB_PHASE void riccati_vector(const Ctx& c, const Inst& I, double delta, double* Qs) { riccati_vector_t<false>(c, I, delta, Qs); }

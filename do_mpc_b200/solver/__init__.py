@@ -51,6 +51,11 @@ def load_library(path):
     lib.dmb_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 15
     lib.dmb_aux_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dp, _c_dp, _c_dp]
     lib.dmb_get_stats.argtypes = [ctypes.c_void_p] + [_c_dp] * 5
+    lib.dmb_set_sens_options.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    lib.dmb_sens_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_int, _c_dp, ctypes.c_int,
+                                  _c_dp, _c_dp, _c_dp]
+    lib.dmb_sens_device.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_int, _c_dp, ctypes.c_int,
+                                    _c_dp, _c_dp, _c_dp, _c_dp]
     return lib
 
 
@@ -191,6 +196,41 @@ class BatchedNlpSolver:
         out = np.zeros((B, self.dims[DIM_NHOR] * self.dims[DIM_NSCEN] * self.n_aux))
         self._check(self.lib.dmb_aux_host(self._h, B, _ptr(x), _ptr(p), _ptr(out)))
         return out[0] if B == 1 else out
+
+    # ---- parametric sensitivities of solved instances (reference: NLPDifferentiator.differentiate) --------------------------
+    def sensitivities(self, x, lam_g, P, status=None, cols=None, u0_only=False, want_dlam=False, active_set_tol=1e-6,
+                      active_weight=1e10, relaxed_bounds_rule=False):
+        """d opt_x (scaled) / d opt_p[cols] at solved instances: x [B,n_w], lam_g [B,n_g], P [B,n_p] as returned by /
+        passed to solve_batch.  Returns dict(dxdp [B, n_w or n_u, ncols], sens_status [B] [, dlamdp [B, n_g+n_w, ncols]])."""
+        x, lam_g, P = _as2d(x, self.n_w), _as2d(lam_g, self.n_g), _as2d(P, self.n_p)
+        B = P.shape[0]
+        cols_a = None if cols is None else np.ascontiguousarray(np.asarray(cols, dtype=np.int32).ravel())
+        nc = self.n_p if cols_a is None else cols_a.size
+        nrow = self.n_u if u0_only else self.n_w
+        dx = np.empty((B, nc, nrow)); sst = np.empty(B, dtype=np.int32)
+        dl = np.empty((B, nc, self.n_g + self.n_w)) if (want_dlam and not u0_only) else None
+        st = None if status is None else np.ascontiguousarray(np.asarray(status, dtype=np.int32).ravel())
+        self._check(self.lib.dmb_set_sens_options(self._h, float(active_set_tol), float(active_weight), int(bool(relaxed_bounds_rule))))
+        self._check(self.lib.dmb_sens_host(self._h, B, _ptr(x), _ptr(lam_g), _ptr(P), _ptr(st), 1 if u0_only else 0, _ptr(cols_a),
+                                           nc, _ptr(dx), _ptr(dl), _ptr(sst)))
+        out = {"dxdp": dx.transpose(0, 2, 1), "sens_status": sst}
+        if dl is not None:
+            out["dlamdp"] = dl.transpose(0, 2, 1)
+        return out
+
+    def sensitivities_device(self, x, lam_g, P, status=None, cols=None, u0_only=True, stream=None):
+        """Device-resident variant (CUDA float64 torch tensors); returns dxdp as [B, ncols, n_u or n_w] (kernel layout)."""
+        import torch
+        B, dev = P.shape[0], P.device
+        def dp(t): return None if t is None else ctypes.c_void_p(t.data_ptr())
+        cols_a = None if cols is None else np.ascontiguousarray(np.asarray(cols, dtype=np.int32).ravel())
+        nc = self.n_p if cols_a is None else cols_a.size
+        dx = torch.empty(B, nc, self.n_u if u0_only else self.n_w, dtype=torch.float64, device=dev)
+        sst = torch.empty(B, dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        self._check(self.lib.dmb_sens_device(self._h, B, dp(x), dp(lam_g), dp(P), dp(status), 1 if u0_only else 0, _ptr(cols_a), nc,
+                                             dp(dx), None, dp(sst), ctypes.c_void_p(st.cuda_stream)))
+        return {"dxdp_t": dx, "sens_status": sst}
 
     def launch_info(self):
         grid = ctypes.c_int(); block = ctypes.c_int(); smem = ctypes.c_int(); n = ctypes.c_longlong(); ms = ctypes.c_float()

@@ -62,18 +62,22 @@ def generate(r: Recipe) -> str:
                    E.emit_c([(f"d[{i}]", e) for i, e in enumerate(nl_ids)], inp) if n_nl else "  (void)d;"))
 
     # ---- Jacobians (structural nonzeros, row-major order) ---------------------------------------------------------
+    theta_ids = list(tv_ids) + list(pp_ids)        # parameters the stage functions depend on (sensitivity right-hand sides)
+    n_th = len(theta_ids)
+
     def jac_nz(rows):
-        nz, r_, c_ = [], [], []
+        nz, r_, c_, dth = [], [], [], []
         for i, ex in enumerate(rows):
-            g = E.gradient(ex, q_ids)
-            for j, d in enumerate(g):
+            g = E.gradient(ex, list(q_ids) + theta_ids)
+            for j, d in enumerate(g[:n_q]):
                 if d != E.ZERO:
                     nz.append(d); r_.append(i); c_.append(j)
-        return nz, r_, c_
-    jn, jr, jc = jac_nz(G_ids)
+            dth.append(g[n_q:])
+        return nz, r_, c_, dth
+    jn, jr, jc, dG_dth = jac_nz(G_ids)
     out.append(_fn("gen_J", sig_args + ", double* __restrict__ jnz",
                    E.emit_c([(f"jnz[{k}]", e) for k, e in enumerate(jn)], inp)))
-    dn, dr, dcol = jac_nz(nl_ids)
+    dn, dr, dcol, dD_dth = jac_nz(nl_ids)
     out.append(_fn("gen_nl_jac", sig_args + ", double* __restrict__ dnz",
                    E.emit_c([(f"dnz[{k}]", e) for k, e in enumerate(dn)], inp) if dn else "  (void)dnz;"))
 
@@ -92,12 +96,13 @@ def generate(r: Recipe) -> str:
     lag_args = sig_args + ", const double* __restrict__ lam, const double sig_l, const double sig_e, const double* __restrict__ lnl"
     out.append(_fn("gen_lag_grad", lag_args + ", double* __restrict__ gq",
                    "  (void)lam; (void)lnl;\n" + E.emit_c([(f"gq[{i}]", e) for i, e in enumerate(gL)], inpL)))
-    hn, hr, hc = [], [], []
+    hn, hr, hc, dgL_dth = [], [], [], []
     for i in range(n_q):
-        row = E.gradient(gL[i], q_ids[:i + 1]) if gL[i] != E.ZERO else [E.ZERO] * (i + 1)
-        for j, d in enumerate(row):
+        row = E.gradient(gL[i], list(q_ids[:i + 1]) + theta_ids) if gL[i] != E.ZERO else [E.ZERO] * (i + 1 + n_th)
+        for j, d in enumerate(row[:i + 1]):
             if d != E.ZERO:
                 hn.append(d); hr.append(i); hc.append(j)
+        dgL_dth.append(row[i + 1:])
     out.append(_fn("gen_lag_hess", lag_args + ", double* __restrict__ hnz",
                    "  (void)lam; (void)lnl; (void)sig_l; (void)sig_e;\n" +
                    (E.emit_c([(f"hnz[{k}]", e) for k, e in enumerate(hn)], inpL) if hn else "  (void)hnz;")))
@@ -172,6 +177,27 @@ def generate(r: Recipe) -> str:
     out.append(_fn("gen_mterm_hess", m_args + ", double* __restrict__ hm",
                    "  (void)x; (void)tvp; (void)pp;\n" +
                    E.emit_c([(f"hm[{i * r.n_x + j}]", HM[i][j]) for i in range(r.n_x) for j in range(r.n_x)], inpM)))
+    # ---- parameter derivatives for the sensitivity right-hand sides (differentiator, _nlpdifferentiator.py:289-304) -------------
+    def switch(cases):
+        if not cases:
+            return "  (void)j;"
+        return "  switch (j) {\n" + "\n".join(f"  case {j}: {{\n{body}\n  }} break;" for j, body in enumerate(cases)) + "\n  default: break;\n  }"
+    cases = []
+    for j in range(n_th):
+        outs = ([(f"dq[{i}]", dgL_dth[i][j]) for i in range(n_q)] + [(f"dG[{i}]", dG_dth[i][j]) for i in range(len(G_ids))] +
+                [(f"dD[{i}]", dD_dth[i][j]) for i in range(n_nl)])
+        cases.append(E.emit_c(outs, inpL))
+    out.append(_fn("gen_dtheta", "const int j, " + lag_args + ", double* __restrict__ dq, double* __restrict__ dG, double* __restrict__ dD",
+                   "  (void)q; (void)tvp; (void)pp; (void)lam; (void)lnl; (void)sig_l; (void)sig_e; (void)dq; (void)dG; (void)dD;\n" + switch(cases)))
+    cases = []
+    for j in range(len(tv_ids)):
+        cases.append(E.emit_c([(f"o[{i}]", E.gradient(g, [tv_ids[j]])[0]) for i, g in enumerate(gR)], inpR))
+    out.append(_fn("gen_rterm_dtvp", "const int j, " + r_args + ", double* __restrict__ o", "  (void)u; (void)up; (void)tvp; (void)o;\n" + switch(cases)))
+    cases = []
+    for j in range(n_th):
+        cases.append(E.emit_c([(f"o[{i}]", E.gradient(g, [theta_ids[j]])[0]) for i, g in enumerate(gM)], inpM))
+    out.append(_fn("gen_mterm_dtheta", "const int j, " + m_args + ", double* __restrict__ o", "  (void)x; (void)tvp; (void)pp; (void)o;\n" + switch(cases)))
+
     # ---- aux -------------------------------------------------------------------------------------------------------------------------
     aux_ids = r.aux.ids()
     out.append(_fn("gen_aux", sig_args + ", double* __restrict__ a",
@@ -189,7 +215,7 @@ def generate(r: Recipe) -> str:
                 NY=r.n_y, NNODE=n_node, NEDGE=len(r.edge_k), NHOR=r.N, NW=r.n_w, NG=r.n_g, NP=r.n_p,
                 NAUX=len(aux_ids), DISCRETE=int(r.discrete), P_X0=r.p_x0, P_TVP=r.p_tvp, P_P=r.p_p, P_UPREV=r.p_uprev,
                 NNZ_J=len(jn), NNZ_H=len(hn), NNZ_D=len(dn), HAS_DUMMIES=has_dummies, NPZ=r.Pz, NPC=r.P,
-                NSCEN=r.n_comb ** r.n_robust)
+                NSCEN=r.n_comb ** r.n_robust, NTHETA=n_th)
     for k, v in dims.items():
         H.append(f"#define DMB_{k} {v}")
     H.append(f"#define NLAM_ACTIVE {r.n_g}")

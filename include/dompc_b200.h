@@ -15,6 +15,8 @@
  *                                    the reference is single-instance, host only)
  *   dmb_get_stats                <-> S.stats()                                    do_mpc/optimizer.py:778
  *   dmb_aux_host                 <-> opt_aux_expression_fun(opt_x, opt_p)         do_mpc/controller/_mpc.py:1331
+ *   dmb_sens_host / _device      <-> NLPDifferentiator.differentiate(nlp_sol, p)  do_mpc/differentiator/_nlpdifferentiator.py:682-741
+ *                                    (d x_opt / d p and d lam / d p of solved instances; active_set_tol as settings.active_set_tol)
  *
  * Layouts: all vectors are the reference's flat vectors: opt_x (n_w, scaled
  * variables), opt_p (n_p), g / lam_g (n_g), row-major over the batch: element i of instance b at [b*n + i].
@@ -78,6 +80,23 @@ int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s
 
 /* aux expressions at every (k, scenario): aux [B, n_horizon * n_scenarios * n_aux] from x [B,n_w], p [B,n_p] (host) */
 int dmb_aux_host(dmb_solver* s, int B, const double* x, const double* p, double* aux);
+
+/* Parametric sensitivities of solved instances (call after a solve, with its x / lam_g / p / status).
+ * mode DMB_SENS_FULL: dx [B, ncols, n_w] = d opt_x(scaled) / d opt_p[col], dlam [B, ncols, n_g + n_w] (lam_g | lam_x) or NULL;
+ * mode DMB_SENS_U0  : dx [B, ncols, n_u] = d u_0(scaled) / d opt_p[col], dlam ignored.
+ * cols: HOST array of opt_p indices (NULL = all n_p columns).  status: solver status per instance or NULL; instances that
+ * were not solved get NaN and sens_status DMB_SENS_SKIPPED.  sens_status: 0 ok, 1 ok but the reduced Hessian
+ * on the active set is indefinite, 2 failed (singular system), 3 skipped. */
+#define DMB_SENS_FULL 0
+#define DMB_SENS_U0 1
+/* relaxed_bounds_rule = 0 (default): a bound is active when |x - bound| <= active_set_tol for the USER's bound, exactly the
+ * reference's test (_nlpdifferentiator.py:345-375); 1: measured against the relaxed bound the interior-point method
+ * worked with (bound_relax_factor) — differs when |bound| * 1e-8 > active_set_tol, i.e. for unscaled bounds > 100. */
+int dmb_set_sens_options(dmb_solver* s, double active_set_tol /* 1e-6 */, double active_weight /* 1e10 */, int relaxed_bounds_rule);
+int dmb_sens_device(dmb_solver* s, int B, const double* d_x, const double* d_lam_g, const double* d_p, const int* d_status,
+                    int mode, const int* cols, int ncols, double* d_dx, double* d_dlam, int* d_sens_status, void* cuda_stream);
+int dmb_sens_host(dmb_solver* s, int B, const double* x, const double* lam_g, const double* p, const int* status, int mode,
+                  const int* cols, int ncols, double* dx, double* dlam, int* sens_status);
 
 /* launch geometry of the last solve and number of kernel launches issued by this handle so far */
 int dmb_get_stats(dmb_solver* s, int* grid, int* block, int* smem_bytes, long long* n_launches, float* last_kernel_ms);

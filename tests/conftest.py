@@ -30,7 +30,7 @@ def build_hostsim(recipe, tag):
     src = generate(recipe)
     csrc = ROOT / "do_mpc_b200" / "csrc"
     h = hashlib.sha256(src.encode())
-    for f in ("ipm_core.cuh", "ipm_solve.cuh", "dmb_host_util.h"):
+    for f in ("ipm_core.cuh", "ipm_solve.cuh", "ipm_refine.cuh", "ipm_sens.cuh", "dmb_host_util.h"):
         h.update((csrc / f).read_bytes())
     h.update((ROOT / "tests" / "hostsim" / "hostsim.cpp").read_bytes())
     d = ROOT / "tests" / "hostsim" / "_build" / f"{tag}_{h.hexdigest()[:12]}"
@@ -86,6 +86,20 @@ class HostSim:
             out["x"][:, ~used] = xg[:, ~used]
         out["success"] = (out["status"] == 0) | (out["status"] == 1)
         return out
+
+    def sens(self, x, lam_g, P, cols=None, tol=1e-6, big=1e10, want_dlam=False, relaxed_rule=0):
+        """dx [B, ncols, n_w] (scaled opt_x) / d opt_p[col] at solved instances (same phases as dmb_sens_kernel)."""
+        import ctypes
+        r = self.r
+        x = np.ascontiguousarray(x, dtype=float); lam_g = np.ascontiguousarray(lam_g, dtype=float)
+        P = np.ascontiguousarray(P, dtype=float); B = P.shape[0]
+        cols = np.arange(r.n_p, dtype=np.int32) if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+        dx = np.zeros((B, len(cols), r.n_w)); sst = np.zeros(B, np.int32)
+        dl = np.zeros((B, len(cols), r.n_g + r.n_w)) if want_dlam else None
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.hostsim_sens(B, p(x), p(lam_g), p(P), p(self.lbx), p(self.ubx), ctypes.byref(self.o), ctypes.c_double(tol),
+                              ctypes.c_double(big), int(relaxed_rule), p(cols), len(cols), p(dx), p(dl), p(sst))
+        return (dx, dl, sst) if want_dlam else (dx, sst)
 
     def w2flat(self):
         import re

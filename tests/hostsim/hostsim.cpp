@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <vector>
 #include "ipm_solve.cuh"
+#include "ipm_sens.cuh"
 #include "dmb_host_util.h"
 
 extern "C" {
@@ -43,6 +44,35 @@ int hostsim_solve(int B, const double* x_init, const double* x0s, const double* 
     if (status) status[b] = r.status;
     if (iters) iters[b] = r.iters;
     if (u0) for (int i = 0; i < NX * 0 + NU; ++i) u0[(size_t)b * NU + i] = I.w[NODE_OFF(0) + NX + i];
+  }
+  return 0;
+}
+
+// sensitivities of solved instances (same phases as dmb_sens_kernel).  dx [B, ncols, n_w], dlam [B, ncols, n_g+n_w] or NULL
+int hostsim_sens(int B, const double* x, const double* lam_g, const double* p, const double* lbx, const double* ubx,
+                 const DmbOptions* opts, double tol, double big, int rule, const int* cols, int ncols, double* dx, double* dlam, int* sstat) {
+  std::vector<double> lbI(NWI), ubI(NWI), vec(WV_END), er((size_t)NEDGE * ER_SZ), node((size_t)NNODE * WN_NODE),
+      eb((size_t)NEDGE * EB_SZ);
+  std::vector<double> tile((size_t)TILE_SZ + 1), Qs(DMB_QS_SIZE), lb0(NWI), ub0(NWI);
+  dmb_internal_bounds(lbx, ubx, opts, lbI.data(), ubI.data());
+  DmbOptions o0 = *opts; o0.bound_relax_factor = 0.0;
+  dmb_internal_bounds(lbx, ubx, &o0, lb0.data(), ub0.data());
+  Ctx c{0, 1, 0, 0, 1, 0, 0, 1};
+  DmbShared S;
+  for (int b = 0; b < B; ++b) {
+    Inst I;
+    bind_vectors(I, vec.data());
+    I.er = er.data(); I.node = node.data(); I.eb = eb.data();
+    I.p = p + (size_t)b * DMB_NP; I.lb = lbI.data(); I.ub = ubI.data(); I.df = 1.0; I.sub = nullptr;
+    I.relax_fac = opts->bound_relax_factor; I.relax_max = opts->constr_viol_tol;
+    sstat[b] = sens_factor(c, I, x + (size_t)b * DMB_NW, lam_g + (size_t)b * DMB_NG, rule ? lbI.data() : lb0.data(),
+                           rule ? ubI.data() : ub0.data(), rule, tol, big, tile.data(), Qs.data(), &S);
+    if (sstat[b] >= DMB_SENS_FAILED) continue;
+    for (int jc = 0; jc < ncols; ++jc) {
+      sens_rhs(c, I, cols[jc]);
+      sens_solve(c, I, opts->max_refine, opts->residual_ratio_max, tile.data(), Qs.data(), &S);
+      sens_store(c, I, 0, dx + ((size_t)b * ncols + jc) * DMB_NW, dlam ? dlam + ((size_t)b * ncols + jc) * (DMB_NG + DMB_NW) : nullptr);
+    }
   }
   return 0;
 }
