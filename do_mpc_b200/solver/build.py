@@ -27,7 +27,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 def _kernel_sources_digest() -> str:
     h = hashlib.sha256()
-    for f in ("ipm_core.cuh", "ipm_solve.cuh", "dmb_api.cu", "dmb_host_util.h"):
+    for f in ("ipm_core.cuh", "ipm_solve.cuh", "ipm_refine.cuh", "ipm_sens.cuh", "dmb_api.cu", "dmb_host_util.h"):
         h.update((CSRC / f).read_bytes())
     h.update((INCLUDE / "dompc_b200.h").read_bytes())
     return h.hexdigest()
@@ -54,24 +54,50 @@ def _sizes(r: Recipe, src: str, threads: int):
     return tiles + qs + 128, ern, vec
 
 
-def launch_config(r: Recipe, src: str):
-    """(threads per CTA, reduced blocks + node data in shared memory?, iterate vectors in shared memory?, CTAs/SM the
-    register budget is compiled for).  227 KB of shared memory per SM on sm_100; measured on B200 (cfg #2): 3 CTAs/SM
-    with the iterate vectors in the L1/L2-backed slot beat 2 CTAs/SM with everything on chip (132.6k vs 110.6k solves/s)."""
-    threads = int(os.environ.get("DMB_FORCE_THREADS", "128"))     # override: tuning experiments only
+def _config_for(r: Recipe, src: str, threads: int):
     fixed, ern, vec = _sizes(r, src, threads)
-    if 8 * fixed > 150 * 1024:
-        threads = 64
-        fixed, ern, vec = _sizes(r, src, threads)
-    if 8 * fixed > 220 * 1024:
-        raise NotImplementedError(f"problem too large for the shared-memory tiles of the solver ({8 * fixed} bytes per CTA)")
     kb = lambda d: 8 * d / 1024.0
     ern_smem = int(kb(fixed + ern) <= 110)
     vec_smem = int(ern_smem and kb(fixed + ern + vec) <= 73)
     if "DMB_FORCE_VEC_SMEM" in os.environ:                 # tuning experiments only
         vec_smem = int(os.environ["DMB_FORCE_VEC_SMEM"])
     total = kb(fixed + (ern if ern_smem else 0) + (vec if vec_smem else 0)) + 1
-    min_ctas = max(1, min(4, int(227 // total)))
+    return fixed, ern_smem, vec_smem, total
+
+
+def launch_config(r: Recipe, src: str):
+    """(threads per CTA, reduced blocks + node data in shared memory?, iterate vectors in shared memory?, CTAs/SM the
+    register budget is compiled for).  227 KB of shared memory per SM on sm_100.  Measured on B200 (cfg #2):
+      * 3 CTAs/SM with the iterate vectors in the L1/L2-backed slot beat 2 CTAs/SM with everything on chip (132.6k vs 110.6k),
+      * the factor and recovery phases process the edges in rounds of (threads / GSZ) lane groups: 160 threads = 10 groups
+        finish the 20 edges of cfg #2 in 2 full rounds instead of 3 (8 + 8 + 4) with 128 threads: 137.8k vs 127.5k solves/s
+        at the same 3 CTAs/SM (registers capped at 128 instead of 168; the extra spills cost less than the idle round).
+    Rule: 128 threads unless the edges fit in few rounds (<= 6 with 128 threads); then the warp-multiple CTA size with the
+    fewest rounds among those that keep the CTAs/SM of the 128-thread build (shared memory and a 128-register budget).
+    Problems with many edges (scenario trees: cfg #3 270 edges, cfg #5 180) measured faster with 128 threads and more
+    CTAs (3301 vs 2794, 1248 vs 1216 solves/s) — the round granularity does not matter there."""
+    n_edge = len(r.edge_k)
+    gsz = 16 if r.n_y <= 16 else 32
+
+    def cfg(threads):
+        fixed, ern_smem, vec_smem, total = _config_for(r, src, threads)
+        if 8 * fixed > 220 * 1024 or total > 226:
+            return None
+        ctas = max(1, min(4, int(227 // total), 65536 // (threads * 128)))
+        return (-(-n_edge // (threads // gsz)), threads, ern_smem, vec_smem, ctas)
+
+    if "DMB_FORCE_THREADS" in os.environ:                  # tuning experiments only
+        best = cfg(int(os.environ["DMB_FORCE_THREADS"]))
+    else:
+        best = cfg(128) or cfg(64)
+        if best is not None and best[1] == 128 and best[0] <= 6:
+            for threads in (160, 192, 224, 256):
+                c = cfg(threads)
+                if c is not None and c[4] >= min(best[4], 3) and c[0] < best[0]:
+                    best = c
+    if best is None:
+        raise NotImplementedError("problem too large for the shared-memory tiles of the solver")
+    _, threads, ern_smem, vec_smem, min_ctas = best
     if "DMB_FORCE_MIN_CTAS" in os.environ:
         min_ctas = int(os.environ["DMB_FORCE_MIN_CTAS"])
     return threads, ern_smem, vec_smem, min_ctas
