@@ -115,3 +115,39 @@ def test_batched_sampler_reproduces_reference_dataset_table(mpc, dataset):
     assert np.abs(df["iter_count"].to_numpy()[ok] - dataset["iter_count"][:200][ok]).max() <= 1
     p2 = sampling_plan_box(mpc, 16, seed=42)
     assert len(p2) == 16 and p2[0]["x0"].shape == (4, 1) and np.all(p2[3]["u_prev"].ravel() <= [100, 0])
+
+
+def test_ampc_sampler_open_and_closed_loop_feed_the_trainer(mpc, tmp_path):
+    """reference workflow (documentation/.../approximate_mpc notebooks): AMPCSampler -> data_<name>_opt.pkl -> Trainer -> ApproxMPC."""
+    import pandas as pd
+    from do_mpc_b200.approximateMPC import AMPCSampler, ApproxMPC, Trainer
+    box = dict(lbx=[0.1, 0.1, 50.0, 50.0], ubx=[2.0, 2.0, 140.0, 140.0])
+    s = AMPCSampler(mpc)
+    s.settings.n_samples, s.settings.dataset_name, s.settings.data_dir, s.settings.seed = 256, "ol", str(tmp_path), 3
+    s.settings.lbx, s.settings.ubx = box["lbx"], box["ubx"]
+    s.setup()
+    df = s.default_sampling()
+    assert len(df) == 256 and list(df.columns) == ["x0", "u_prev", "id", "u0", "status", "t_make_step", "t_wall", "iter_count"]
+    opt = pd.read_pickle(tmp_path / "ol" / "data_ol_opt.pkl")
+    assert 0.4 * 256 < len(opt) < 256 and opt["status"].all()
+    c = AMPCSampler(mpc)
+    c.settings.n_samples, c.settings.dataset_name, c.settings.data_dir, c.settings.seed = 64, "cl", str(tmp_path), 4
+    c.settings.closed_loop_flag, c.settings.trajectory_length = True, 4
+    c.settings.lbx, c.settings.ubx = box["lbx"], box["ubx"]
+    c.setup()
+    dfc = c.default_sampling()
+    assert 64 < len(dfc) <= 256                         # trajectories stop at their first failed solve
+    # consecutive samples of one trajectory: x0 of step k+1 is the simulated successor, u_prev the applied input
+    t0 = dfc[dfc["id"].str.endswith("_0") & dfc["status"]].iloc[0]
+    t1 = dfc[dfc["id"] == t0["id"][:-2] + "_1"].iloc[0]
+    assert np.allclose(t1["u_prev"], t0["u0"]) and not np.allclose(t1["x0"], t0["x0"])
+    a = ApproxMPC(mpc)
+    a.settings.n_hidden_layers, a.settings.n_neurons = 2, 24
+    a.settings.lbx, a.settings.ubx = box["lbx"], box["ubx"]
+    a.setup()
+    t = Trainer(a)
+    t.settings.dataset_name, t.settings.n_epochs, t.settings.data_dir, t.settings.print_frequency = "ol", 30, str(tmp_path), 1000
+    t.setup()
+    h = t.default_training()
+    assert h["train_loss"][-1] < h["train_loss"][0]
+    assert a.make_step(np.array([[0.8], [0.4], [134.0], [130.0]])).shape == (2, 1)
