@@ -224,7 +224,7 @@ class AMPCSampler:
             if k + 1 < steps:
                 # the reference stops a trajectory at the first failed solve (_ampc_sampler.py:440-447)
                 alive &= ok
-                Xn = self.simulator.make_step_batch(X, out["u0"])
+                Xn = self.simulator.make_step_batch(X, out["u0"])[0]
                 U = np.where(alive[:, None], out["u0"], U)
                 X = np.where(alive[:, None], Xn, X)
         df = pd.DataFrame(rows)

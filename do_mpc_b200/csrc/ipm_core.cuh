@@ -181,7 +181,7 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define WV_DS (WV_ST + NEDGE * NNL)
 #define WV_VU (WV_DS + NEDGE * NNL)
 #define WV_END (WV_VU + NEDGE * NNL)
-#define DMB_QS_SIZE (NXI * NVP + NXI + 8 + (NNODE + 2) / 2)        // + per-node ready counters (ints) of the pipelined sweep
+#define DMB_QS_SIZE (NXI * NVP + NXI + 8)
 
 #ifdef DMB_HOSTSIM
 #define DMB_CLOCK() 0LL
@@ -891,26 +891,9 @@ template <bool LDL>
 DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
   CTA_SYNC();                       // every thread has consumed the flag of a previous call before it is reset
   if (c.tid == 0) *flag = 0;
-  // The assembly of the node matrices (1) and the serial sweep (2) are pipelined on the device: warps 1.. assemble the
-  // nodes from the end of the horizon backwards and publish a per-node entry count; warp 0 starts sweeping as soon as the
-  // last stage is complete and otherwise only waits for the node it is about to reduce (the assembly is ~3x faster than
-  // the sweep, so it disappears from the critical path; r1d cycle counters: 6.7 % of the CTA time).
-#ifdef DMB_HOSTSIM
-  const bool pipelined = false;
-  const int a_tid = c.tid, a_n = c.nthr;
-#else
-  int* ready = reinterpret_cast<int*>(Qs + NXI * NVP + NXI + 8);
-  const bool pipelined = c.nwarp > 1;
-  if (pipelined) {
-    for (int n = c.tid; n < NNODE; n += c.nthr) ready[n] = 0;
-    CTA_SYNC();
-  }
-  const int a_tid = pipelined ? c.tid - 32 : c.tid, a_n = pipelined ? c.nthr - 32 : c.nthr;
-#endif
   // ---- (1) node matrices ------------------------------------------------------------------------------------------
-  for (int idx = a_tid; idx >= 0 && idx < NNODE * (NV * NV + NV); idx += a_n) {
-    const int n_seq = idx / (NV * NV + NV), ent = idx - n_seq * (NV * NV + NV);
-    const int n = pipelined ? NNODE - 1 - n_seq : n_seq;
+  for (int idx = c.tid; idx < NNODE * (NV * NV + NV); idx += c.nthr) {
+    const int n = idx / (NV * NV + NV), ent = idx - n * (NV * NV + NV);
     double* wn = I.node + (size_t)n * WN_NODE;
     const int k = DMB_NODE_K[n];
     const bool is_q = ent >= NV * NV;
@@ -956,31 +939,20 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         }
     }
     wn[WN_Q + ent] = val;
-#ifndef DMB_HOSTSIM
-    if (pipelined) { __threadfence_block(); atomicAdd(&ready[n], 1); }
-#endif
   }
-  if (!pipelined) CTA_SYNC();
+  CTA_SYNC();
   SUB_START();
   // ---- (2) sweep ----------------------------------------------------------------------------------------------------------
   if (c.warp == 0) {
     double* W = Qs;                  // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
     double* pb = Qs + NXI * NVP;     // NXI       : p_c + P_c[:, x] b
-#ifndef DMB_HOSTSIM
-#define DMB_WAIT_NODE(nn) do { if (pipelined) { if (c.lane == 0) { while (((volatile int*)ready)[nn] < NV * NV + NV) { } } \
-                                 __syncwarp(); __threadfence_block(); } } while (0)
-#else
-#define DMB_WAIT_NODE(nn) ((void)0)
-#endif
     for (int n = NNODE - 1; n >= 0; --n) {
       if (DMB_NODE_K[n] == NHOR) continue;
       double* wn = I.node + (size_t)n * WN_NODE;
-      DMB_WAIT_NODE(n);
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
         const double* er = I.er + (size_t)e * ER_SZ;
         const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
-        if (DMB_NODE_K[DMB_EDGE_CHILD[e]] == NHOR) DMB_WAIT_NODE(DMB_EDGE_CHILD[e]);
         for (int idx = c.lane; idx < NXI * NVP + NXI; idx += DMB_LANES) {
           if (idx < NXI * NVP) {
             const int r = idx / NVP, jj = idx - r * NVP;
