@@ -851,6 +851,15 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 //        W = P_c [A B]_aug , Q += [A B]_aug' W , Cholesky of Q_uu , K = -Q_uu^{-1} Q_u. , P = Q_xx + Q_xu K (in place).
 // *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
+// lower-triangle index -> (row i >= column j)
+#define NTRI_VP (NVP * (NVP + 1) / 2)
+#define NTRI_XI (NXI * (NXI + 1) / 2)
+DMB_DEV void tri_decode(int idx, int& i, int& j) {
+  int r = 0;
+  while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+  i = r; j = idx - r * (r + 1) / 2;
+}
+
 // unpivoted L D L' of the control block (row stride NV): strict lower part of L (unit diagonal), diagonal = 1 / D.
 // returns bit 0: zero / non-finite pivot (replaced by 1), bit 1: negative pivot.
 DMB_DEV int quu_ldl(const double* Quu, double* L) {
@@ -946,6 +955,8 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
   if (c.warp == 0) {
     double* W = Qs;                  // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
     double* pb = Qs + NXI * NVP;     // NXI       : p_c + P_c[:, x] b
+    int tvi, tvj, txi, txj;          // this lane's first lower-triangle entry of the two symmetric updates (loop invariant)
+    tri_decode(c.lane, tvi, tvj); tri_decode(c.lane, txi, txj);
     for (int n = NNODE - 1; n >= 0; --n) {
       if (DMB_NODE_K[n] == NHOR) continue;
       double* wn = I.node + (size_t)n * WN_NODE;
@@ -969,15 +980,18 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
           }
         }
         WARP_SYNC();
-        for (int idx = c.lane; idx < NVP * NVP + NVP; idx += DMB_LANES) {
-          if (idx < NVP * NVP) {
-            const int i = idx / NVP, jj = idx - i * NVP;
+        // [A B]' W is symmetric: only the lower triangle is formed (one lane pass for NVP <= 7) and mirrored
+        for (int idx = c.lane; idx < NTRI_VP + NVP; idx += DMB_LANES) {
+          if (idx < NTRI_VP) {
+            int i, jj;
+            if (idx == c.lane) { i = tvi; jj = tvj; } else tri_decode(idx, i, jj);
             double s = (i >= NX && i < NX + NU) ? W[(NX + i - NX) * NVP + jj] : 0.0;
 #pragma unroll
             for (int r = 0; r < NX; ++r) s += er[ER_AB + r * NVP + i] * W[r * NVP + jj];
             wn[WN_Q + VPOS(i) * NV + VPOS(jj)] += s;
+            if (i != jj) wn[WN_Q + VPOS(jj) * NV + VPOS(i)] += s;
           } else {
-            const int i = idx - NVP * NVP;
+            const int i = idx - NTRI_VP;
             double s = (i >= NX && i < NX + NU) ? pb[NX + i - NX] : 0.0;
 #pragma unroll
             for (int r = 0; r < NX; ++r) s += er[ER_AB + r * NVP + i] * pb[r];
@@ -1020,15 +1034,18 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         }
       }
       WARP_SYNC();
-      for (int idx = c.lane; idx < NXI * NXI + NXI; idx += DMB_LANES) {
-        if (idx < NXI * NXI) {
-          const int a = idx / NXI, b = idx - a * NXI;
+      // P = Q_xixi + Q_xiu K is symmetric as well: lower triangle, mirrored
+      for (int idx = c.lane; idx < NTRI_XI + NXI; idx += DMB_LANES) {
+        if (idx < NTRI_XI) {
+          int a, b;
+          if (idx == c.lane) { a = txi; b = txj; } else tri_decode(idx, a, b);
           double s = wn[WN_Q + a * NV + b];
 #pragma unroll
           for (int t = 0; t < NUT; ++t) s += wn[WN_Q + a * NV + NXI + t] * wn[WN_K + t * NXI + b];
           wn[WN_Q + a * NV + b] = s;
+          if (a != b) wn[WN_Q + b * NV + a] = s;
         } else {
-          const int a = idx - NXI * NXI;
+          const int a = idx - NTRI_XI;
           double s = wn[WN_QV + a];
 #pragma unroll
           for (int t = 0; t < NUT; ++t) s += wn[WN_Q + a * NV + NXI + t] * wn[WN_KV + t];
