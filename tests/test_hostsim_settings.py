@@ -1,0 +1,75 @@
+"""Controller settings the reference exposes (do_mpc/controller/_mpcsettings.py): every discretisation / constraint option that
+changes the NLP is run through the kernel's algorithm source (CPU emulation) and compared with the oracle IPM on the
+oracle's independent restatement of the same NLP — sizes, return status, iteration count, first input."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, HostSim, cstr_batch_inputs
+from oracle import models
+from oracle.ipm import IPMSolver, IpmOptions, solve_mpc
+from oracle.nlp import FlatNLP
+
+N = 6
+VARIANTS = {
+    "deg3": dict(collocation_deg=3),
+    "deg1": dict(collocation_deg=1),
+    "ni2": dict(collocation_ni=2),
+    "deg3_ni2": dict(collocation_deg=3, collocation_ni=2),
+    "legendre": dict(collocation_type="legendre"),
+    "horizon1": dict(n_horizon=1),
+    "no_colloc_bounds": dict(cons_check_colloc_points=False),
+    "terminal_bounds": dict(use_terminal_bounds=True),
+    "hard_nl_cons_colloc": dict(nl_cons_check_colloc_points=True),
+    "soft_nl_cons": dict(),
+}
+
+
+def _build(name):
+    import cstr
+    kw = dict(VARIANTS[name])
+    n_hor = kw.pop("n_horizon", N)
+    mpc = cstr.cstr_nominal_mpc(n_horizon=n_hor, setup=False)
+    for k, v in kw.items():
+        setattr(mpc.settings, k, v)
+    if name == "terminal_bounds":
+        mpc.terminal_bounds["upper", "_x", "C_b"] = 1.2
+    if name == "hard_nl_cons_colloc":
+        mpc.set_nl_cons("T_K_hard", mpc.model.x["T_K"] - 0.5 * mpc.model.x["T_R"], ub=70.0)
+    if name == "soft_nl_cons":
+        mpc.set_nl_cons("T_R_soft", mpc.model.x["T_R"], ub=132.0, soft_constraint=True, penalty_term_cons=50.0)
+    mpc.prepare_nlp()
+    d = dataclasses.replace(models.cstr_nominal(n_hor), **kw)
+    if name == "hard_nl_cons_colloc":
+        d = dataclasses.replace(d, nl_cons=[models.NlCons("T_K_hard", d.model.x[3] - 0.5 * d.model.x[2], ub=70.0)])
+    if name == "soft_nl_cons":
+        d = dataclasses.replace(d, nl_cons=[models.NlCons("T_R_soft", d.model.x[2], ub=132.0, soft=True, penalty=50.0)])
+    if name == "terminal_bounds":
+        # only C_b gets a terminal upper bound: the other entries stay +inf (the default "terminal = state bounds" applies
+        # only while NO terminal bound is set, reference _mpc.py:914-918), the untouched lower bounds default to x_lb
+        d = dataclasses.replace(d, x_terminal_ub=np.array([np.inf, 1.2, np.inf, np.inf]), x_terminal_lb=None)
+    return mpc, FlatNLP(d)
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_setting_variant_matches_oracle(name):
+    mpc, nlp = _build(name)
+    r = mpc.recipe
+    assert (r.n_w, r.n_g, r.n_p) == (nlp.n_w, nlp.n_g, nlp.n_p)
+    lbx, ubx = mpc._lb_opt_x.full().ravel(), mpc._ub_opt_x.full().ravel()
+    assert np.array_equal(np.nan_to_num(lbx, neginf=-1e30), np.nan_to_num(nlp.lbx, neginf=-1e30))
+    assert np.array_equal(np.nan_to_num(ubx, posinf=1e30), np.nan_to_num(nlp.ubx, posinf=1e30))
+    d = np.load(GOLDEN / "cstr_dataset.npz")
+    idx = np.where(d["success"])[0][[0, 3, 7]]
+    P, x0s, u0s = cstr_batch_inputs(r, d["x0"][idx], d["u_prev"][idx])
+    sim = HostSim(mpc, "cstr_" + name)
+    out = sim.solve(P, x0s, u0s)
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
+    for b, i in enumerate(idx):
+        ro = solve_mpc(nlp, d["x0"][i], d["u_prev"][i], solver=orc)
+        assert bool(out["success"][b]) == ro["success"], (name, i, out["status"][b], ro["return_status"])
+        if ro["success"]:
+            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= 1, (name, i)
+            assert np.abs(out["u0_scaled"][b] - ro["u0"] / r.u_scaling).max() < 1e-7, (name, i)
+            assert np.abs(out["x"][b] - ro["x"])[nlp.used_mask()].max() < 1e-6
