@@ -81,3 +81,24 @@ def test_industrial_poly_matches_reference_on_gpu():
     assert out["status"][0] in (0, 1) and out["success"][0]
     assert np.abs(out["u0_scaled"][0] - g["u"][0] / r.u_scaling).max() < TOL
     assert np.abs(out["g"][0]).max() < 1e-7
+
+
+@pytest.mark.parametrize("name", ["deg3_ni2", "legendre", "horizon1", "hard_nl_cons_colloc", "soft_nl_cons", "terminal_bounds"])
+def test_setting_variants_on_the_gpu_match_the_oracle(name):
+    """The settings sweep of tests/test_hostsim_settings.py through the real kernel + C ABI (each variant is its own generated library)."""
+    from test_hostsim_settings import _build
+    from conftest import GOLDEN, cstr_batch_inputs
+    from oracle.ipm import IPMSolver, IpmOptions, solve_mpc
+    mpc, nlp = _build(name)
+    mpc.create_nlp()
+    r = mpc.recipe
+    d = np.load(GOLDEN / "cstr_dataset.npz")
+    idx = np.where(d["success"])[0][[0, 3, 7, 11]]
+    out = mpc.make_step_batch(d["x0"][idx], d["u_prev"][idx])
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
+    for b, i in enumerate(idx):
+        ro = solve_mpc(nlp, d["x0"][i], d["u_prev"][i], solver=orc)
+        assert bool(out["success"][b]) == ro["success"], (name, i)
+        if ro["success"]:
+            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= 1
+            assert np.abs((out["u0"][b] - ro["u0"]) / r.u_scaling).max() < 1e-7
