@@ -12,6 +12,7 @@ from . import controller as _controller_mod
 from . import casadi_api
 from . import sampling
 from . import approximateMPC
+from . import rollout
 from . import differentiator as _diff_mod
 from . import simulator as _sim_mod
 from . import estimator as _est_mod

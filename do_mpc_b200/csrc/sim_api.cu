@@ -39,6 +39,19 @@ void dms_destroy(dms_sim* s) { if (!s) return; cudaSetDevice(s->device); cudaFre
 const char* dms_last_error(dms_sim* s) { return s ? s->err.c_str() : "null handle"; }
 long long dms_launch_count(dms_sim* s) { return s ? s->n_launches : 0; }
 
+int dms_step_device(dms_sim* s, int B, const double* d_x, const double* d_u, const double* d_z, const double* d_tvp, const double* d_p,
+                    double t_step, int n_sub, double newton_tol, int newton_max, int mode,
+                    double* d_x_next, double* d_z_next, double* d_aux, int* d_status, void* stream_) {
+  if (!s || B <= 0 || !d_x || !d_x_next || !d_status || (DMS_NU && !d_u) || (SNZ && (!d_z || !d_z_next)) || (DMS_NTVP && !d_tvp) ||
+      (DMS_NPM && !d_p)) return -2;
+  CK(cudaSetDevice(s->device));
+  dms_step_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(B, d_x, d_u, d_z, d_tvp, d_p, t_step, n_sub, newton_tol, newton_max, mode,
+                                                                  d_x_next, d_z_next, d_aux, d_status);
+  CK(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
 int dms_step_host(dms_sim* s, int B, const double* x, const double* u, const double* z, const double* tvp, const double* pp,
                   double t_step, int n_sub, double newton_tol, int newton_max, int mode,
                   double* x_next, double* z_next, double* aux, int* status) {

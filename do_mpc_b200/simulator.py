@@ -45,6 +45,8 @@ def _load(path):
     lib.dms_launch_count.argtypes = [ctypes.c_void_p]
     lib.dms_step_host.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5 + \
         [ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
+    lib.dms_step_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5 + \
+        [ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
     return lib
 
 
@@ -145,6 +147,29 @@ class Simulator:
         pp = np.tile(self.p_fun(self._t0).full().ravel(), (B, 1)) if (p is None and m.n_p) else p
         xn, zn, _, st = self._call(X, U, Z, tv, pp, 0)
         return xn, zn, st
+
+    def make_step_batch_device(self, X, U, Z=None, tvp=None, p=None, out=None, stream=None):
+        """Device-resident step: CUDA float64 torch tensors in, dict(x, z, status) of CUDA tensors out; queued on `stream`
+        (default: torch's current stream), no host synchronisation."""
+        import torch
+        m, s = self.model, self.settings
+        B, dev = X.shape[0], X.device
+        dp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        if m.n_tvp and tvp is None:
+            tvp = torch.as_tensor(self.tvp_fun(self._t0).full().ravel(), dtype=torch.float64, device=dev).repeat(B, 1)
+        if m.n_p and p is None:
+            p = torch.as_tensor(self.p_fun(self._t0).full().ravel(), dtype=torch.float64, device=dev).repeat(B, 1)
+        if m.n_z and Z is None:
+            Z = torch.as_tensor(self._z0.full().ravel(), dtype=torch.float64, device=dev).repeat(B, 1)
+        if out is None:
+            out = {"x": torch.empty(B, m.n_x, dtype=torch.float64, device=dev), "z": torch.empty(B, max(m.n_z, 1), dtype=torch.float64, device=dev),
+                   "status": torch.empty(B, dtype=torch.int32, device=dev)}
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.dms_step_device(self._h, B, dp(X), dp(U), dp(Z), dp(tvp), dp(p), float(s.t_step), int(s.n_substeps), float(s.newton_tol),
+                                      int(s.newton_max_iter), 0, dp(out["x"]), dp(out["z"]), None, dp(out["status"]), ctypes.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"do_mpc_b200 simulator error {rc}: {self.lib.dms_last_error(self._h).decode()}")
+        return out
 
     def init_algebraic_variables(self) -> NumStruct:
         if self.model.n_z == 0:

@@ -21,6 +21,10 @@ long long dms_launch_count(dms_sim* s);
 int dms_step_host(dms_sim* s, int B, const double* x, const double* u, const double* z, const double* tvp, const double* p,
                   double t_step, int n_sub, double newton_tol, int newton_max, int mode,
                   double* x_next, double* z_next, double* aux /* may be NULL */, int* status);
+/* same step with device-resident arrays, queued on cuda_stream (no reference counterpart: the reference is host only) */
+int dms_step_device(dms_sim* s, int B, const double* d_x, const double* d_u, const double* d_z, const double* d_tvp, const double* d_p,
+                    double t_step, int n_sub, double newton_tol, int newton_max, int mode,
+                    double* d_x_next, double* d_z_next, double* d_aux /* may be NULL */, int* d_status, void* cuda_stream);
 #ifdef __cplusplus
 }
 #endif

@@ -56,3 +56,19 @@ def test_no_gpu_means_loud_failure_not_fallback(lib_path):
     mpc = cstr.cstr_nominal_mpc(setup=False)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         mpc.setup()
+
+
+def test_simulator_library_exports_every_declared_symbol():
+    import cstr
+    from do_mpc_b200.solver.build import build_sim_library
+    hdr = (ROOT / "include" / "dompc_b200_sim.h").read_text()
+    names = set(re.findall(r"\b(dms_[a-z_]+)\s*\(", hdr))
+    assert {"dms_create", "dms_destroy", "dms_step_host", "dms_step_device", "dms_get_dims", "dms_last_error"} <= names
+    lib = ctypes.CDLL(str(build_sim_library(cstr.cstr_model(False))))
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dompc_b200_sim.h but not exported"
+    d = (ctypes.c_int * 8)()
+    lib.dms_get_dims(d)
+    assert list(d)[:3] == [4, 2, 0]
+    lib.dms_create.restype = ctypes.c_void_p
+    assert not lib.dms_create(0)          # no GPU here: loud failure, no fallback

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import do_mpc_b200 as do_mpc
+from conftest import GOLDEN
 from examples_common import EXAMPLES, golden
 
 pytestmark = pytest.mark.gpu
@@ -44,3 +45,28 @@ def test_five_closed_loop_steps_match_reference_goldens(name):
     assert np.abs((mpc.data["_u"][0] - g["u"][0]) / su).max() < 1e-6            # cold-start step: same path as IPOPT
     assert np.abs(sim.data["_x"] - g["x"]).max() / (1 + np.abs(g["x"]).max()) < 1e-5
     assert mpc.data["success"].min() == 1.0
+
+
+def test_device_resident_closed_loop_equals_the_host_loop():
+    """do_mpc_b200.rollout.closed_loop_device (solve kernel -> integrator kernel, no host round trip) against the reference-style
+    Python loop make_step / simulator.make_step / estimator.make_step, instance by instance."""
+    import cstr
+    from do_mpc_b200.rollout import closed_loop_device
+    d = np.load(GOLDEN / "cstr_dataset.npz")
+    idx = np.where(d["success"])[0][:6]
+    mpc = cstr.cstr_nominal_mpc()
+    sim = do_mpc.simulator.Simulator(mpc.model); sim.set_param(t_step=mpc.settings.t_step); sim.setup()
+    T = 4
+    res = closed_loop_device(mpc, sim, d["x0"][idx], T, U_prev=d["u_prev"][idx])
+    assert res["x"].shape == (T + 1, 6, 4) and res["u"].shape == (T, 6, 2) and np.all(res["status"] == 0)
+    r = mpc.recipe
+    for b, i in enumerate(idx[:3]):
+        mpc.reset_history(); sim.reset_history()
+        x0 = d["x0"][i].reshape(-1, 1)
+        mpc.x0 = x0; mpc.u0 = d["u_prev"][i].reshape(-1, 1); sim.x0 = x0
+        mpc.set_initial_guess()
+        for k in range(T):
+            u0 = mpc.make_step(x0)
+            x0 = sim.make_step(u0)
+            assert np.abs((u0.ravel() - res["u"][k, b]) / r.u_scaling).max() < 1e-6, (b, k)
+            assert np.abs((x0.ravel() - res["x"][k + 1, b]) / r.x_scaling).max() < 1e-7, (b, k)
