@@ -43,7 +43,7 @@
 
 struct KernelArgs {
   int B;
-  const double *x_init, *x0s, *u0s, *z0s, *p, *lbI, *ubI;
+  const double *x_init, *x0s, *u0s, *z0s, *p, *lbI, *ubI, *lam_g0, *lam_x0;
   double *x, *lam_g, *lam_x, *g, *f, *u0, *stats, *ws;
   int *status, *iters, *counter;
   DmbOptions o;
@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
     I.p = a.p + (size_t)b * DMB_NP;
     load_initial_guess(c, a.x_init ? a.x_init + (size_t)b * DMB_NW : nullptr, a.x0s ? a.x0s + (size_t)b * NX : nullptr,
                        a.u0s ? a.u0s + (size_t)b * NU : nullptr, a.z0s ? a.z0s + (size_t)b * DMB_NZ : nullptr, I.wt);
-    solve_instance(c, I, a.o, I.wt, sm + SM_TILE, sm + SM_QS, S, &result);
+    solve_instance(c, I, a.o, I.wt, sm + SM_TILE, sm + SM_QS, S, &result, a.lam_g0 ? a.lam_g0 + (size_t)b * DMB_NG : nullptr,
+                   a.lam_x0 ? a.lam_x0 + (size_t)b * DMB_NW : nullptr);
     const double df = result.df;
     if (a.x && a.x_init)
       for (int i = c.tid; i < DMB_NW; i += c.nthr) a.x[(size_t)b * DMB_NW + i] = a.x_init[(size_t)b * DMB_NW + i];
@@ -278,10 +279,12 @@ int dmb_set_bounds(dmb_solver* s, const double* lbx, const double* ubx) {
   return DMB_E_OK;
 }
 
-int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double* d_x0s, const double* d_u0s,
-                     const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x, double* d_g,
-                     double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* stream_) {
+int dmb_solve_device_ws(dmb_solver* s, int B, const double* d_x_init, const double* d_lam_g0, const double* d_lam_x0, const double* d_x0s,
+                        const double* d_u0s, const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x,
+                        double* d_g, double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* stream_) {
   if (!s) return DMB_E_ARG;
+  if ((d_lam_g0 || d_lam_x0) && (!d_lam_g0 || !d_lam_x0 || !d_x_init)) { s->err = "warm start needs x_init, lam_g0 and lam_x0 together"; return DMB_E_ARG; }
+  if ((d_lam_g0 && d_lam_g0 == d_lam_g) || (d_lam_x0 && d_lam_x0 == d_lam_x)) { s->err = "warm-start multipliers must not alias the outputs"; return DMB_E_ARG; }
   if (B <= 0 || !d_p || !d_f || !d_status || !d_iters || !d_u0 || (!d_x_init && (!d_x0s || !d_u0s)) ||
       (!d_x_init && DMB_NZ > 0 && !d_z0s)) { s->err = "invalid argument"; return DMB_E_ARG; }
   if (!s->have_bounds) { s->err = "dmb_set_bounds must be called before solving"; return DMB_E_STATE; }
@@ -289,6 +292,7 @@ int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double*
   CK(cudaSetDevice(s->device));
   CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), st));
   KernelArgs a;
+  a.lam_g0 = d_lam_g0; a.lam_x0 = d_lam_x0;
   a.B = B; a.x_init = d_x_init; a.x0s = d_x0s; a.u0s = d_u0s; a.z0s = d_z0s; a.p = d_p; a.lbI = s->d_lbI; a.ubI = s->d_ubI;
   a.x = d_x; a.lam_g = d_lam_g; a.lam_x = d_lam_x; a.g = d_g; a.f = d_f; a.u0 = d_u0; a.stats = d_stats; a.ws = s->d_ws;
   a.status = d_status; a.iters = d_iters; a.counter = s->d_counter; a.o = s->opts;
@@ -306,6 +310,13 @@ int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double*
   return DMB_E_OK;
 }
 
+int dmb_solve_device(dmb_solver* s, int B, const double* d_x_init, const double* d_x0s, const double* d_u0s,
+                     const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x, double* d_g,
+                     double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* stream_) {
+  return dmb_solve_device_ws(s, B, d_x_init, nullptr, nullptr, d_x0s, d_u0s, d_z0s, d_p, d_x, d_lam_g, d_lam_x, d_g, d_f, d_status, d_iters,
+                             d_u0, d_stats, stream_);
+}
+
 static int ensure_stage(dmb_solver* s, size_t doubles) {
   if (doubles > s->stage_doubles) {
     cudaFree(s->d_stage); s->d_stage = nullptr; s->stage_doubles = 0;
@@ -318,6 +329,12 @@ static int ensure_stage(dmb_solver* s, size_t doubles) {
 int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s,
                    const double* p, double* x, double* lam_g, double* lam_x, double* g, double* f, int* status,
                    int* iters, double* u0, double* stats) {
+  return dmb_solve_host_ws(s, B, x_init, nullptr, nullptr, x0s, u0s, z0s, p, x, lam_g, lam_x, g, f, status, iters, u0, stats);
+}
+
+int dmb_solve_host_ws(dmb_solver* s, int B, const double* x_init, const double* lam_g0, const double* lam_x0, const double* x0s,
+                      const double* u0s, const double* z0s, const double* p, double* x, double* lam_g, double* lam_x, double* g,
+                      double* f, int* status, int* iters, double* u0, double* stats) {
   if (!s) return DMB_E_ARG;
   if (B <= 0 || !p || !f || !status || !iters || !u0) { s->err = "invalid argument"; return DMB_E_ARG; }
   CK(cudaSetDevice(s->device));
@@ -328,16 +345,19 @@ int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s
   const size_t o_p = take(nB * DMB_NP), o_xi = take(x_init ? nB * DMB_NW : 0), o_x0 = take(x0s ? nB * NX : 0),
                o_u0s = take(u0s ? nB * NU : 0), o_z0 = take(z0s ? nB * DMB_NZ : 0), o_x = take(x ? nB * DMB_NW : 0),
                o_lg = take(lam_g ? nB * DMB_NG : 0), o_lx = take(lam_x ? nB * DMB_NW : 0), o_g = take(g ? nB * DMB_NG : 0),
-               o_f = take(nB), o_u = take(nB * NU), o_st = take(stats ? nB * DMB_NSTAT : 0), o_i1 = take(nB), o_i2 = take(nB);
+               o_f = take(nB), o_u = take(nB * NU), o_st = take(stats ? nB * DMB_NSTAT : 0), o_i1 = take(nB), o_i2 = take(nB),
+               o_lg0 = take(lam_g0 ? nB * DMB_NG : 0), o_lx0 = take(lam_x0 ? nB * DMB_NW : 0);
   int rc = ensure_stage(s, off);
   if (rc) return rc;
   double* d = s->d_stage;
   CK(cudaMemcpyAsync(d + o_p, p, nB * DMB_NP * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (x_init) CK(cudaMemcpyAsync(d + o_xi, x_init, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (lam_g0) CK(cudaMemcpyAsync(d + o_lg0, lam_g0, nB * DMB_NG * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (lam_x0) CK(cudaMemcpyAsync(d + o_lx0, lam_x0, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (x0s) CK(cudaMemcpyAsync(d + o_x0, x0s, nB * NX * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (u0s) CK(cudaMemcpyAsync(d + o_u0s, u0s, nB * NU * sizeof(double), cudaMemcpyHostToDevice, 0));
   if (z0s && DMB_NZ > 0) CK(cudaMemcpyAsync(d + o_z0, z0s, nB * DMB_NZ * sizeof(double), cudaMemcpyHostToDevice, 0));
-  rc = dmb_solve_device(s, B, x_init ? d + o_xi : nullptr, x0s ? d + o_x0 : nullptr, u0s ? d + o_u0s : nullptr,
+  rc = dmb_solve_device_ws(s, B, x_init ? d + o_xi : nullptr, lam_g0 ? d + o_lg0 : nullptr, lam_x0 ? d + o_lx0 : nullptr, x0s ? d + o_x0 : nullptr, u0s ? d + o_u0s : nullptr,
                         (z0s && DMB_NZ > 0) ? d + o_z0 : nullptr, d + o_p, x ? d + o_x : nullptr, lam_g ? d + o_lg : nullptr,
                         lam_x ? d + o_lx : nullptr, g ? d + o_g : nullptr, d + o_f, (int*)(d + o_i1), (int*)(d + o_i2),
                         d + o_u, stats ? d + o_st : nullptr, nullptr);

@@ -21,6 +21,7 @@ static inline void dmb_fill_default_options(DmbOptions* o) {
   o->nlp_scaling_max_gradient = 100.0; o->nlp_scaling_min_value = 1e-8; o->kappa_resto = 0.9;
   o->max_iter = 3000; o->acceptable_iter = 15; o->max_soc = 4; o->mimic_dummy_reg = 1; o->resto_max_iter = 60;
   o->warm_start = 0; o->residual_ratio_max = 1e-10; o->max_refine = 4; o->pad_ = 0;
+  o->ws_bound_push = 1e-3; o->ws_bound_frac = 1e-3; o->ws_mult_bound_push = 1e-3; o->ws_mult_init_max = 1e6;   // IPOPT warm_start_* defaults
 }
 
 // flat bounds (scaled variables, reference order) -> internal layout with IPOPT's bound relaxation.

@@ -60,6 +60,7 @@ struct DmbOptions {
   double alpha_min_frac, delta, kappa_soc;
   double delta_w_first, delta_w_min, delta_w_max, kappa_w_plus_first, kappa_w_plus, kappa_w_minus;
   double nlp_scaling_max_gradient, nlp_scaling_min_value, kappa_resto, residual_ratio_max;
+  double ws_bound_push, ws_bound_frac, ws_mult_bound_push, ws_mult_init_max;   // warm_start_* (used when warm_start != 0)
   int max_iter, acceptable_iter, max_soc, mimic_dummy_reg, resto_max_iter, warm_start, max_refine, pad_;
 };
 

@@ -80,8 +80,12 @@ DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, dou
   *s_c = fmax(s_max, SZ / fmax(NZ, 1.0)) / s_max;
 }
 
+// lam_g0 / lam_x0 (flat reference layouts, may be NULL): the multipliers of a previous solution; used only with
+// o.warm_start (IPOPT warm_start_init_point=yes: the point is pushed by warm_start_bound_push/frac, the multipliers are taken
+// over — bound multipliers at least warm_start_mult_bound_push —, no least-squares estimate, mu starts at mu_init).
 DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o, const double* x0_internal,
-                            double* tile, double* Qs, DmbShared* S, DmbResult* out) {
+                            double* tile, double* Qs, DmbShared* S, DmbResult* out,
+                            const double* lam_g0 = nullptr, const double* lam_x0 = nullptr) {
   Inst I = I_in;
   double* red = S->red;
 #ifdef DMB_PROFILE
@@ -123,21 +127,48 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   }
   CTA_SYNC();
   // ---- starting point: push into the (relaxed) bounds, slacks, bound multipliers ----------------------------
+  const bool ws = o.warm_start != 0 && lam_g0 != nullptr && lam_x0 != nullptr;
+  const double bpush = ws ? o.ws_bound_push : o.bound_push, bfrac = ws ? o.ws_bound_frac : o.bound_frac;
   for (int i = c.tid; i < NWI; i += c.nthr) {
     const double lo = I.lb[i], hi = I.ub[i];
     const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
     double v = I.w[i];
     if (hl && hu) {
-      const double pl = fmin(o.bound_push * fmax(1.0, fabs(lo)), o.bound_frac * (hi - lo));
-      const double pu = fmin(o.bound_push * fmax(1.0, fabs(hi)), o.bound_frac * (hi - lo));
+      const double pl = fmin(bpush * fmax(1.0, fabs(lo)), bfrac * (hi - lo));
+      const double pu = fmin(bpush * fmax(1.0, fabs(hi)), bfrac * (hi - lo));
       v = fmin(fmax(v, lo + pl), hi - pu);
-    } else if (hl) v = fmax(v, lo + o.bound_push * fmax(1.0, fabs(lo)));
-    else if (hu) v = fmin(v, hi - o.bound_push * fmax(1.0, fabs(hi)));
+    } else if (hl) v = fmax(v, lo + bpush * fmax(1.0, fabs(lo)));
+    else if (hu) v = fmin(v, hi - bpush * fmax(1.0, fabs(hi)));
     I.w[i] = v;
-    I.zL[i] = hl ? o.bound_mult_init_val : 0.0;
-    I.zU[i] = hu ? o.bound_mult_init_val : 0.0;
+    double zl = o.bound_mult_init_val, zu = o.bound_mult_init_val;
+    if (ws) {
+      const int fl = DMB_W2FLAT[i];
+      const double lx = fl >= 0 ? I.df * lam_x0[fl] : 0.0;             // lam_x = zU - zL (unscaled objective)
+      zl = fmin(fmax(-lx, o.ws_mult_bound_push), o.ws_mult_init_max);
+      zu = fmin(fmax(lx, o.ws_mult_bound_push), o.ws_mult_init_max);
+    }
+    I.zL[i] = hl ? zl : 0.0;
+    I.zU[i] = hu ? zu : 0.0;
   }
-  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) { I.s[i] = 0.0; I.vU[i] = o.bound_mult_init_val; }
+  if (ws) {
+    for (int i = c.tid; i < NLAM; i += c.nthr) {
+      const int fl = DMB_LAM2FLAT[i];
+      const double y = fl >= 0 ? I.df * lam_g0[fl] / I.dc[i] : 0.0;
+      I.lam[i] = fmin(fmax(y, -o.ws_mult_init_max), o.ws_mult_init_max);
+    }
+    CTA_SYNC();
+#if DMB_DISCRETE
+    for (int idx = c.tid; idx < NEDGE * NX; idx += c.nthr) {           // auxiliary end-of-interval rows: lam_G = lam_C
+      const int e = idx / NX, i = idx - e * NX;
+      I.lam[LAM_EDGE(e) + DMB_NZ + i] = I.lam[LAM_EDGE(e) + NY + i];
+    }
+#endif
+  }
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    I.s[i] = 0.0;
+    I.vU[i] = ws ? fmin(fmax(I.lam[LAM_EDGE(i / (NNL > 0 ? NNL : 1)) + NY + NX + i % (NNL > 0 ? NNL : 1)], o.ws_mult_bound_push), o.ws_mult_init_max)
+                 : o.bound_mult_init_val;
+  }
   CTA_SYNC();
   double f, theta, inf_pr;
   eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
@@ -147,13 +178,15 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     const int e = i / NNL, j = i % NNL;
     const double d = I.res[LAM_EDGE(e) + NY + NX + j];      // s was 0
     const double hi = nl_ub_relaxed(I, e, j);
-    I.s[i] = fmin(d, hi - o.bound_push * fmax(1.0, fabs(hi)));
+    I.s[i] = fmin(d, hi - bpush * fmax(1.0, fabs(hi)));
   }
   CTA_SYNC();
   eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
 #endif
-  // ---- least-squares multiplier estimate ----------------------------------------------------------------------------
   if (c.tid == 0) { S->fail = 0; S->n_filt = 0; }
+  CTA_SYNC();
+  if (!ws) {
+  // ---- least-squares multiplier estimate ----------------------------------------------------------------------------
   for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = 0.0;
   CTA_SYNC();
   eval_derivatives(c, I);                       // lam = 0: objective gradient and Jacobian at the pushed point
@@ -168,6 +201,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     for (int i = c.tid; i < NLAM; i += c.nthr) I.lam[i] = ok ? I.lamn[i] : 0.0;
   }
   CTA_SYNC();
+  }
 
   DMB_TICK(8);
   double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);

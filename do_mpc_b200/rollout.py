@@ -40,7 +40,10 @@ def closed_loop_device(mpc, simulator, X0, n_steps: int, U_prev=None, warm_start
         P[:, r.p_x0:r.p_x0 + r.n_x] = x
         P[:, r.p_uprev:r.p_uprev + r.n_u] = up
         if warm_start and out is not None:
-            out = S.solve_batch_device(P, x_init=out["x"].clone(), out=out, want_full=True)
+            # with ipopt.warm_start_init_point=yes the previous multipliers are taken over as well (copies: no aliasing with the outputs)
+            ws = bool(S.options.warm_start)
+            out = S.solve_batch_device(P, x_init=out["x"].clone(), out=out, want_full=True,
+                                       lam_g0=out["lam_g"].clone() if ws else None, lam_x0=out["lam_x"].clone() if ws else None)
         else:
             out = S.solve_batch_device(P, x0s=x * xs, u0s=up / us, want_full=True)
         u = out["u0_scaled"] * us

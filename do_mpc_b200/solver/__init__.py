@@ -49,6 +49,8 @@ def load_library(path):
     lib.dmb_set_bounds.argtypes = [ctypes.c_void_p, _c_dp, _c_dp]
     lib.dmb_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 14
     lib.dmb_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 15
+    lib.dmb_solve_host_ws.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 16
+    lib.dmb_solve_device_ws.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_c_dp] * 17
     lib.dmb_aux_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dp, _c_dp, _c_dp]
     lib.dmb_get_stats.argtypes = [ctypes.c_void_p] + [_c_dp] * 5
     lib.dmb_set_sens_options.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]
@@ -118,8 +120,9 @@ class BatchedNlpSolver:
             self._bounds_key = key
 
     # ---- batched host entry point --------------------------------------------------------------------------------
-    def solve_batch(self, P, x0s=None, u0s=None, z0s=None, lbx=None, ubx=None, x_init=None, return_full=False):
-        """P [B,n_p]; initial guess = x_init [B,n_w] (scaled) or broadcast of x0s,u0s,z0s (scaled). Host arrays."""
+    def solve_batch(self, P, x0s=None, u0s=None, z0s=None, lbx=None, ubx=None, x_init=None, return_full=False, lam_g0=None, lam_x0=None):
+        """P [B,n_p]; initial guess = x_init [B,n_w] (scaled) or broadcast of x0s,u0s,z0s (scaled). Host arrays.
+        lam_g0 / lam_x0: multipliers of a previous solution, used only with the option warm_start (ipopt.warm_start_init_point)."""
         P = _as2d(P, self.n_p)
         B = P.shape[0]
         if lbx is not None:
@@ -128,13 +131,16 @@ class BatchedNlpSolver:
         x0s = None if x0s is None else _as2d(x0s, self.n_x)
         u0s = None if u0s is None else _as2d(u0s, self.n_u)
         z0s = None if (z0s is None or self.n_z == 0) else _as2d(z0s, self.n_z)
+        use_ws = bool(self.options.warm_start) and lam_g0 is not None and lam_x0 is not None and x_init is not None
+        lam_g0 = _as2d(lam_g0, self.n_g) if use_ws else None
+        lam_x0 = _as2d(lam_x0, self.n_w) if use_ws else None
         f = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
         u0 = np.empty((B, self.n_u)); stats = np.empty((B, NSTAT))
         x = lam_g = lam_x = g = None
         if return_full:
             x = np.empty((B, self.n_w)); lam_g = np.empty((B, self.n_g)); lam_x = np.empty((B, self.n_w)); g = np.empty((B, self.n_g))
         t0 = time.perf_counter()
-        rc = self.lib.dmb_solve_host(self._h, B, _ptr(x_init), _ptr(x0s), _ptr(u0s), _ptr(z0s), _ptr(P), _ptr(x),
+        rc = self.lib.dmb_solve_host_ws(self._h, B, _ptr(x_init), _ptr(lam_g0), _ptr(lam_x0), _ptr(x0s), _ptr(u0s), _ptr(z0s), _ptr(P), _ptr(x),
                                      _ptr(lam_g), _ptr(lam_x), _ptr(g), _ptr(f), _ptr(status), _ptr(iters), _ptr(u0), _ptr(stats))
         self._check(rc)
         t = time.perf_counter() - t0
@@ -145,7 +151,7 @@ class BatchedNlpSolver:
         return out
 
     # ---- device-resident entry point (torch tensors as memory containers) ----------------------------------------------
-    def solve_batch_device(self, P, x0s=None, u0s=None, z0s=None, x_init=None, out=None, stream=None, want_full=False):
+    def solve_batch_device(self, P, x0s=None, u0s=None, z0s=None, x_init=None, out=None, stream=None, want_full=False, lam_g0=None, lam_x0=None):
         """All arguments are CUDA float64 torch tensors on this solver's device; returns dict of CUDA tensors.
         Asynchronous with respect to the host (kernel queued on `stream` or the current torch stream)."""
         import torch
@@ -163,7 +169,9 @@ class BatchedNlpSolver:
                            lam_x=torch.empty(B, self.n_w, dtype=torch.float64, device=dev),
                            g=torch.empty(B, self.n_g, dtype=torch.float64, device=dev))
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        rc = self.lib.dmb_solve_device(self._h, B, dp(x_init), dp(x0s), dp(u0s), dp(z0s), dp(P), dp(out.get("x")),
+        if not (self.options.warm_start and lam_g0 is not None and lam_x0 is not None and x_init is not None):
+            lam_g0 = lam_x0 = None
+        rc = self.lib.dmb_solve_device_ws(self._h, B, dp(x_init), dp(lam_g0), dp(lam_x0), dp(x0s), dp(u0s), dp(z0s), dp(P), dp(out.get("x")),
                                        dp(out.get("lam_g")), dp(out.get("lam_x")), dp(out.get("g")), dp(out["f"]),
                                        dp(out["status"]), dp(out["iter_count"]), dp(out["u0_scaled"]), dp(out["stats"]),
                                        ctypes.c_void_p(st.cuda_stream))
@@ -173,13 +181,15 @@ class BatchedNlpSolver:
     # ---- nlpsol-Function look-alike ------------------------------------------------------------------------------------------------
     def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_x0=None, lam_g0=None):
         """Single-instance call with the keyword signature of the CasADi nlpsol Function (optimizer.py:754-770).
-        lam_x0/lam_g0 are accepted and ignored exactly like IPOPT without warm_start_init_point."""
+        lam_x0/lam_g0 are used with ipopt.warm_start_init_point=yes and ignored otherwise, like IPOPT."""
         def arr(v):
             return np.asarray(v.full() if hasattr(v, "full") else v, dtype=np.float64).ravel()
         x0, p = arr(x0), arr(p)
         if x0.size != self.n_w or p.size != self.n_p:
             raise ValueError(f"nlpsol call: x0 has {x0.size} (expected {self.n_w}), p has {p.size} (expected {self.n_p})")
-        r = self.solve_batch(p[None, :], x_init=x0[None, :], lbx=arr(lbx), ubx=arr(ubx), return_full=True)
+        ws = bool(self.options.warm_start) and lam_x0 is not None and lam_g0 is not None
+        r = self.solve_batch(p[None, :], x_init=x0[None, :], lbx=arr(lbx), ubx=arr(ubx), return_full=True,
+                             lam_g0=arr(lam_g0)[None, :] if ws else None, lam_x0=arr(lam_x0)[None, :] if ws else None)
         st = int(r["status"][0])
         self._stats = {"success": bool(r["success"][0]), "return_status": _STATUS_NAMES.get(st, str(st)),
                        "iter_count": int(r["iter_count"][0]), "t_wall_total": r["t_wall_total"],

@@ -9,7 +9,8 @@ _D = ["tol", "dual_inf_tol", "constr_viol_tol", "compl_inf_tol",
       "alpha_red_factor", "eta_phi", "theta_max_fact", "theta_min_fact", "s_phi", "s_theta", "gamma_phi", "gamma_theta",
       "alpha_min_frac", "delta", "kappa_soc",
       "delta_w_first", "delta_w_min", "delta_w_max", "kappa_w_plus_first", "kappa_w_plus", "kappa_w_minus",
-      "nlp_scaling_max_gradient", "nlp_scaling_min_value", "kappa_resto", "residual_ratio_max"]
+      "nlp_scaling_max_gradient", "nlp_scaling_min_value", "kappa_resto", "residual_ratio_max",
+      "ws_bound_push", "ws_bound_frac", "ws_mult_bound_push", "ws_mult_init_max"]
 _I = ["max_iter", "acceptable_iter", "max_soc", "mimic_dummy_reg", "resto_max_iter", "warm_start", "max_refine", "pad_"]
 
 
@@ -26,16 +27,21 @@ IPOPT_MAP = {
     "ipopt.bound_frac": "bound_frac", "ipopt.bound_relax_factor": "bound_relax_factor",
     "ipopt.max_soc": "max_soc", "ipopt.nlp_scaling_max_gradient": "nlp_scaling_max_gradient",
     "ipopt.kappa_d": "kappa_d", "ipopt.tau_min": "tau_min", "ipopt.s_max": "s_max",
+    "ipopt.warm_start_bound_push": "ws_bound_push", "ipopt.warm_start_bound_frac": "ws_bound_frac",
+    "ipopt.warm_start_slack_bound_push": "ws_bound_push", "ipopt.warm_start_slack_bound_frac": "ws_bound_frac",
+    "ipopt.warm_start_mult_bound_push": "ws_mult_bound_push", "ipopt.warm_start_mult_init_max": "ws_mult_init_max",
 }
 IGNORED_PREFIXES = ("ipopt.print_level", "ipopt.sb", "print_time", "ipopt.linear_solver", "expand", "ipopt.hsllib",
-                    "ipopt.print_", "ipopt.output_file", "ipopt.file_print_level", "verbose", "ipopt.warm_start",
+                    "ipopt.print_", "ipopt.output_file", "ipopt.file_print_level", "verbose",
                     "ipopt.ma", "ipopt.mumps", "record_time", "ipopt.timing_statistics", "ipopt.print_timing_statistics")
 
 
 def apply_nlpsol_opts(opts_struct: DmbOptions, nlpsol_opts: dict):
     import warnings
     for k, v in (nlpsol_opts or {}).items():
-        if k in IPOPT_MAP:
+        if k == "ipopt.warm_start_init_point":
+            opts_struct.warm_start = int(str(v).lower() in ("yes", "true", "1"))
+        elif k in IPOPT_MAP:
             f = IPOPT_MAP[k]
             setattr(opts_struct, f, int(v) if f in _I else float(v))
         elif k.startswith("dmb."):

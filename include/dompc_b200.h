@@ -78,6 +78,17 @@ int dmb_solve_host(dmb_solver* s, int B, const double* x_init, const double* x0s
                    const double* p, double* x, double* lam_g, double* lam_x, double* g, double* f, int* status,
                    int* iters, double* u0, double* stats);
 
+/* The same calls with the multipliers of a previous solution (`lam_g0` [B,n_g], `lam_x0` [B,n_w], reference sign convention)
+ * — what optimizer.solve() passes as lam_g0= / lam_x0= (do_mpc/optimizer.py:760-768).  They are used only when the option
+ * warm_start is set (IPOPT: warm_start_init_point yes, with warm_start_bound_push / _frac / _mult_bound_push / _mult_init_max
+ * and mu_init), otherwise ignored exactly like IPOPT ignores them.  Require x_init. */
+int dmb_solve_device_ws(dmb_solver* s, int B, const double* d_x_init, const double* d_lam_g0, const double* d_lam_x0, const double* d_x0s,
+                        const double* d_u0s, const double* d_z0s, const double* d_p, double* d_x, double* d_lam_g, double* d_lam_x,
+                        double* d_g, double* d_f, int* d_status, int* d_iters, double* d_u0, double* d_stats, void* cuda_stream);
+int dmb_solve_host_ws(dmb_solver* s, int B, const double* x_init, const double* lam_g0, const double* lam_x0, const double* x0s,
+                      const double* u0s, const double* z0s, const double* p, double* x, double* lam_g, double* lam_x, double* g,
+                      double* f, int* status, int* iters, double* u0, double* stats);
+
 /* aux expressions at every (k, scenario): aux [B, n_horizon * n_scenarios * n_aux] from x [B,n_w], p [B,n_p] (host) */
 int dmb_aux_host(dmb_solver* s, int B, const double* x, const double* p, double* aux);
 

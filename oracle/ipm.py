@@ -86,6 +86,12 @@ class IpmOptions:
     kappa_resto: float = 0.9
     mimic_dummy_reg: bool = True
     verbose: bool = False
+    # warm start (IPOPT warm_start_init_point = yes; defaults of the warm_start_* options)
+    warm_start_init_point: bool = False
+    warm_start_bound_push: float = 1e-3
+    warm_start_bound_frac: float = 1e-3
+    warm_start_mult_bound_push: float = 1e-3
+    warm_start_mult_init_max: float = 1e6
 
 
 def _inertia_from_sytrf(ldu, ipiv):
@@ -212,16 +218,19 @@ class IPMSolver:
         self.dL, self.dU, self.jL, self.jU = dL, dU, jL, jU
 
         # -- starting point ---------------------------------------------------------------------
+        ws = bool(o.warm_start_init_point) and lam_g0 is not None and lam_x0 is not None
+        b_push, b_frac = (o.warm_start_bound_push, o.warm_start_bound_frac) if ws else (o.bound_push, o.bound_frac)
+
         def push(v, lo, hi):
             v = v.copy()
             both = np.isfinite(lo) & np.isfinite(hi)
             onlyl = np.isfinite(lo) & ~np.isfinite(hi)
             onlyu = ~np.isfinite(lo) & np.isfinite(hi)
-            pl = np.minimum(o.bound_push * np.maximum(1.0, np.abs(lo[both])), o.bound_frac * (hi[both] - lo[both]))
-            pu = np.minimum(o.bound_push * np.maximum(1.0, np.abs(hi[both])), o.bound_frac * (hi[both] - lo[both]))
+            pl = np.minimum(b_push * np.maximum(1.0, np.abs(lo[both])), b_frac * (hi[both] - lo[both]))
+            pu = np.minimum(b_push * np.maximum(1.0, np.abs(hi[both])), b_frac * (hi[both] - lo[both]))
             v[both] = np.minimum(np.maximum(v[both], lo[both] + pl), hi[both] - pu)
-            v[onlyl] = np.maximum(v[onlyl], lo[onlyl] + o.bound_push * np.maximum(1.0, np.abs(lo[onlyl])))
-            v[onlyu] = np.minimum(v[onlyu], hi[onlyu] - o.bound_push * np.maximum(1.0, np.abs(hi[onlyu])))
+            v[onlyl] = np.maximum(v[onlyl], lo[onlyl] + b_push * np.maximum(1.0, np.abs(lo[onlyl])))
+            v[onlyu] = np.minimum(v[onlyu], hi[onlyu] - b_push * np.maximum(1.0, np.abs(hi[onlyu])))
             return v
         x = push(x, xL, xU)
         c, d = self._eval_g(x)
@@ -233,9 +242,17 @@ class IPMSolver:
 
         grad = self._eval_grad(x)
         Jc, Jd = self._eval_jac(x)
-        # least-squares multiplier estimate
+        # least-squares multiplier estimate (cold start) / user multipliers (warm start)
         yc, yd = np.zeros(m_c), np.zeros(m_d)
-        if m_c + m_d > 0:
+        if ws:
+            lam_g0 = np.asarray(lam_g0, dtype=float).ravel(); lam_x0 = np.asarray(lam_x0, dtype=float).ravel()
+            clip = lambda v: np.minimum(np.maximum(v, o.warm_start_mult_bound_push), o.warm_start_mult_init_max)
+            lx = self.df * lam_x0[self.iv]                       # lam_x = zU - zL of the unscaled problem
+            zL, zU = clip(-lx[iL]), clip(lx[iU])
+            yc = np.clip(self.df * lam_g0[self.ic] / self.dc, -o.warm_start_mult_init_max, o.warm_start_mult_init_max)
+            yd = np.clip(self.df * lam_g0[self.id] / self.dd, -o.warm_start_mult_init_max, o.warm_start_mult_init_max)
+            vL, vU = clip(-yd[jL]), clip(yd[jU])
+        elif m_c + m_d > 0:
             rx = grad.copy(); rx[iL] -= zL; rx[iU] += zU
             rs = np.zeros(m_d); rs[jL] -= vL; rs[jU] += vU
             K = self._assemble(sp.csr_matrix((n, n)), np.ones(n), np.ones(m_d), Jc, Jd, 0.0)

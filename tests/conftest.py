@@ -59,16 +59,16 @@ class HostSim:
         self.lbx = np.ascontiguousarray(mpc._lb_opt_x.full().ravel())
         self.ubx = np.ascontiguousarray(mpc._ub_opt_x.full().ravel())
 
-    def solve(self, P, x0s=None, u0s=None, z0s=None, x_init=None):
+    def solve(self, P, x0s=None, u0s=None, z0s=None, x_init=None, lam_g0=None, lam_x0=None):
         import ctypes
         r = self.r
         P = np.ascontiguousarray(P, dtype=float); B = P.shape[0]
         c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=float)
-        x_init, x0s, u0s, z0s = c(x_init), c(x0s), c(u0s), c(z0s)
+        x_init, x0s, u0s, z0s, lam_g0, lam_x0 = c(x_init), c(x0s), c(u0s), c(z0s), c(lam_g0), c(lam_x0)
         out = dict(x=np.zeros((B, r.n_w)), lam_g=np.zeros((B, r.n_g)), lam_x=np.zeros((B, r.n_w)), g=np.zeros((B, r.n_g)),
                    f=np.zeros(B), status=np.zeros(B, np.int32), iter_count=np.zeros(B, np.int32), u0_scaled=np.zeros((B, r.n_u)))
         p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
-        self.lib.hostsim_solve(B, p(x_init), p(x0s), p(u0s), p(z0s), p(P), p(self.lbx), p(self.ubx), ctypes.byref(self.o),
+        self.lib.hostsim_solve_ws(B, p(x_init), p(lam_g0), p(lam_x0), p(x0s), p(u0s), p(z0s), p(P), p(self.lbx), p(self.ubx), ctypes.byref(self.o),
                                p(out["x"]), p(out["lam_g"]), p(out["lam_x"]), p(out["g"]), p(out["f"]), p(out["status"]),
                                p(out["iter_count"]), p(out["u0_scaled"]))
         if x_init is None:

@@ -17,9 +17,17 @@ void hostsim_default_options(DmbOptions* o) { dmb_fill_default_options(o); }
 void hostsim_set_verbose(int v) { dmb_hostsim_verbose = v; }
 
 // x_init: [B, n_w] flat scaled initial guess or NULL (then x0s/u0s/z0s broadcast); outputs may be NULL.
+int hostsim_solve_ws(int B, const double* x_init, const double* lam_g0, const double* lam_x0, const double* x0s, const double* u0s,
+                     const double* z0s, const double* p, const double* lbx, const double* ubx, const DmbOptions* opts,
+                     double* x, double* lam_g, double* lam_x, double* g, double* f, int* status, int* iters, double* u0);
 int hostsim_solve(int B, const double* x_init, const double* x0s, const double* u0s, const double* z0s, const double* p,
                   const double* lbx, const double* ubx, const DmbOptions* opts,
                   double* x, double* lam_g, double* lam_x, double* g, double* f, int* status, int* iters, double* u0) {
+  return hostsim_solve_ws(B, x_init, nullptr, nullptr, x0s, u0s, z0s, p, lbx, ubx, opts, x, lam_g, lam_x, g, f, status, iters, u0);
+}
+int hostsim_solve_ws(int B, const double* x_init, const double* lam_g0, const double* lam_x0, const double* x0s, const double* u0s,
+                     const double* z0s, const double* p, const double* lbx, const double* ubx, const DmbOptions* opts,
+                     double* x, double* lam_g, double* lam_x, double* g, double* f, int* status, int* iters, double* u0) {
   std::vector<double> lbI(NWI), ubI(NWI), vec(WV_END), er((size_t)NEDGE * ER_SZ), node((size_t)NNODE * WN_NODE),
       eb((size_t)NEDGE * EB_SZ);
   std::vector<double> tile((size_t)TILE_SZ + 1), Qs(DMB_QS_SIZE), x0i(NWI);
@@ -35,7 +43,8 @@ int hostsim_solve(int B, const double* x_init, const double* x0s, const double* 
     load_initial_guess(c, x_init ? x_init + (size_t)b * DMB_NW : nullptr, x0s ? x0s + (size_t)b * DMB_NX : nullptr,
                        u0s ? u0s + (size_t)b * DMB_NU : nullptr, z0s ? z0s + (size_t)b * DMB_NZ : nullptr, x0i.data());
     DmbResult r;
-    solve_instance(c, I, *opts, x0i.data(), tile.data(), Qs.data(), &S, &r);
+    solve_instance(c, I, *opts, x0i.data(), tile.data(), Qs.data(), &S, &r, lam_g0 ? lam_g0 + (size_t)b * DMB_NG : nullptr,
+                   lam_x0 ? lam_x0 + (size_t)b * DMB_NW : nullptr);
     I.df = r.df;
     if (x && x_init) for (int i = 0; i < DMB_NW; ++i) x[(size_t)b * DMB_NW + i] = x_init[(size_t)b * DMB_NW + i];
     store_solution(c, I, r.df, x ? x + (size_t)b * DMB_NW : nullptr, lam_g ? lam_g + (size_t)b * DMB_NG : nullptr,

@@ -151,3 +151,31 @@ def test_ampc_sampler_open_and_closed_loop_feed_the_trainer(mpc, tmp_path):
     h = t.default_training()
     assert h["train_loss"][-1] < h["train_loss"][0]
     assert a.make_step(np.array([[0.8], [0.4], [134.0], [130.0]])).shape == (2, 1)
+
+
+def test_ipopt_warm_start_option_through_the_cabi(dataset):
+    """nlpsol_opts {'ipopt.warm_start_init_point': 'yes', 'ipopt.mu_init': 1e-4}: lam_g0 / lam_x0 are taken over (dmb_solve_host_ws);
+    same KKT point as the cold solve in fewer iterations, and identical to the CPU emulation of the kernel source."""
+    import cstr
+    from conftest import HostSim, cstr_batch_inputs
+    m = cstr.cstr_nominal_mpc(setup=False)
+    m.settings.nlpsol_opts = {"ipopt.warm_start_init_point": "yes", "ipopt.mu_init": 1e-4}
+    m.setup()
+    assert m.S.options.warm_start == 1 and m.S.options.mu_init == 1e-4
+    r = m.recipe
+    idx = np.where(dataset["success"])[0][:64]
+    P, x0s, u0s = cstr_batch_inputs(r, dataset["x0"][idx], dataset["u_prev"][idx])
+    lbx, ubx = m._lb_opt_x.full().ravel(), m._ub_opt_x.full().ravel()
+    m.S.set_options(warm_start=0, mu_init=0.1)
+    first = m.S.solve_batch(P, x0s, u0s, lbx=lbx, ubx=ubx, return_full=True)
+    P2 = P.copy(); P2[:, r.p_x0:r.p_x0 + r.n_x] *= 1.002; P2[:, r.p_uprev:r.p_uprev + r.n_u] = first["u0_scaled"] * r.u_scaling
+    cold = m.S.solve_batch(P2, x_init=first["x"], lbx=lbx, ubx=ubx, return_full=True)
+    m.S.set_options(warm_start=1, mu_init=1e-4)
+    warm = m.S.solve_batch(P2, x_init=first["x"], lam_g0=first["lam_g"], lam_x0=first["lam_x"], lbx=lbx, ubx=ubx, return_full=True)
+    ok = cold["success"] & warm["success"]
+    assert ok.mean() > 0.9
+    assert np.abs(warm["u0_scaled"] - cold["u0_scaled"])[ok].max() < 1e-5
+    assert warm["iter_count"][ok].mean() < 0.6 * cold["iter_count"][ok].mean()
+    sim = HostSim(m, "cstr_nom"); sim.o.warm_start = 1; sim.o.mu_init = 1e-4
+    hs = sim.solve(P2[:8], x_init=first["x"][:8], lam_g0=first["lam_g"][:8], lam_x0=first["lam_x"][:8])
+    assert np.array_equal(hs["iter_count"], warm["iter_count"][:8]) and np.abs(hs["x"] - warm["x"][:8]).max() < 1e-9
