@@ -2,7 +2,7 @@
 (reference do_mpc/__init__.py:103-128).  Subsystems outside the hot path (simulator, estimators, graphics, ...)
 are not provided; accessing them raises with a clear message."""
 import do_mpc_b200 as _b
-from do_mpc_b200 import model, controller, data, simulator, estimator, differentiator, approximateMPC  # noqa: F401
+from do_mpc_b200 import model, controller, data, simulator, estimator, differentiator, approximateMPC, tools  # noqa: F401
 
 __version__ = _b.__version__
 

@@ -13,6 +13,7 @@ from . import casadi_api
 from . import sampling
 from . import approximateMPC
 from . import rollout
+from . import tools
 from . import differentiator as _diff_mod
 from . import simulator as _sim_mod
 from . import estimator as _est_mod
