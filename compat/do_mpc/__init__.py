@@ -14,4 +14,4 @@ class _Missing:
 
 
 graphics = _Missing("graphics")
-sampling = _Missing("sampling")
+from do_mpc_b200 import sampling  # noqa: F401,E402
