@@ -16,63 +16,91 @@
 // |rho|, |sol|, |rhs|.
 // ---------------------------------------------------------------------------------------------------
 DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, double delta,
-                            double* red, double* out) {
+                            double* red, double* out, double* tile_base) {
   double* rd = I.gl; double* rp = I.rest;
   double nrm_rho = 0.0, nrm_sol = 0.0, nrm_rhs = 0.0;
-  for (int e = c.tid; e < NEDGE; e += c.nthr) {
-    double* eb = I.eb + (size_t)e * EB_SZ;
-    const double* dc = I.dc + LAM_EDGE(e);
-    const double* ln = I.lamn + LAM_EDGE(e);
-    const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
-    const double* dy = I.dw + EDGE_OFF(e);
-    double dq[NQ], hq[NQ];
-#pragma unroll
-    for (int i = 0; i < NVP; ++i) dq[i] = dvp[i];
-#pragma unroll
-    for (int i = 0; i < NY; ++i) dq[NVP + i] = dy[i];
-    gen_hmul(eb + EB_HNZ, dq, hq);
-#pragma unroll
-    for (int i = 0; i < NY; ++i) hq[NVP + i] += (eb[EB_SIGY + i] + delta) * dq[NVP + i] + eb[EB_GY + i];
-    // J_G' lam_G+ and J_G dq (row scaled)
-    double jdq[NY > 0 ? NY : 1];
-#pragma unroll
-    for (int i = 0; i < NY; ++i) jdq[i] = 0.0;
-    for (int k = 0; k < DMB_NNZ_J; ++k) {
-      const int r = DMB_J_ROW[k], cq = DMB_J_COL[k];
-      const double a = dc[r] * eb[EB_JNZ + k];
-      hq[cq] += a * ln[r];
-      jdq[r] += a * dq[cq];
-    }
+  // edge-local part, one lane group per edge (r1e profile: with one thread per edge this section kept a single warp busy for
+  // ~4 % of the wall time).  Scratch in the (idle) LU area of the group's tile; rows of H through its CSR view, J dq through
+  // the row-major nonzero order, J' lam through the CSC view (DMB_JC_*).
+  double* T = tile_base + (size_t)c.grp * TILE_SZ;
+  double* dq = T;                               // NQ
+  double* ln = dq + NQ;                         // NY + NX : lam_G+, lam_C+
+  double* jz = ln + NY + NX;                    // NNZ_J   : row-scaled Jacobian nonzeros
+  double* hq = jz + DMB_NNZ_J;                  // NQ
+  double* ydv = hq + NQ;                        // NNL     : y_d+ of the condensed inequality rows
+  double* dz = ydv + NNL;                       // NNZ_D
+  static_assert(2 * NQ + NY + NX + DMB_NNZ_J + NNL + DMB_NNZ_D <= STG_HNZ, "kkt_residual scratch does not fit into the LU area of the tile");
+  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
+    const int e = e0 + c.grp;
+    const bool act = e < NEDGE;
+    double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+    const double* dc = I.dc + LAM_EDGE(act ? e : 0);
+    if (act) {
+      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = val);
+      DMB_COPY_BATCH(DMB_NNZ_J, c.gl, GSZ, eb[EB_JNZ + idx], jz[idx] = dc[DMB_J_ROW[idx]] * val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_GY + idx], T[STG_GY + idx] = val);
+      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
+      const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
+      const double* dy = I.dw + EDGE_OFF(e);
+      for (int i = c.gl; i < NQ; i += GSZ) dq[i] = i < NVP ? dvp[i] : dy[i - NVP];
+      for (int i = c.gl; i < NY + NX; i += GSZ) ln[i] = I.lamn[LAM_EDGE(e) + i];
 #if NNL > 0
-    for (int i = 0; i < NNL; ++i) {
-      double jd = 0.0;
-      for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) jd += eb[EB_DNZ + t] * dq[DMB_D_COL[t]];
-      const double yd = eb[EB_SIGS + i] * jd + eb[EB_RD + i];          // = y_d+ of the condensed system
-      for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) hq[DMB_D_COL[t]] += eb[EB_DNZ + t] * yd;
-      rp[LAM_EDGE(e) + NY + NX + i] = 0.0;                             // eliminated exactly
-    }
+      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) dz[i] = eb[EB_DNZ + i];
 #endif
-    // continuity: + E' lam_C+ on the end-of-interval state, row residual
-    const double* dxc = I.dw + NODE_OFF(DMB_EDGE_CHILD[e]);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      hq[NVP + DMB_XF_SEL[i]] += ln[NY + i];
-      const double r = res[LAM_EDGE(e) + NY + i] + dq[NVP + DMB_XF_SEL[i]] - dxc[i];
-      rp[LAM_EDGE(e) + NY + i] = r;
-      nrm_rho = fmax(nrm_rho, fabs(r));
     }
+    WARP_SYNC();
+#if NNL > 0
+    if (act)
+      for (int i = c.gl; i < NNL; i += GSZ) {
+        double jd = 0.0;
+        for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) jd += dz[t] * dq[DMB_D_COL[t]];
+        ydv[i] = eb[EB_SIGS + i] * jd + eb[EB_RD + i];                    // = y_d+ of the condensed system
+        rp[LAM_EDGE(e) + NY + NX + i] = 0.0;                               // eliminated exactly
+      }
+    WARP_SYNC();
+#endif
+    if (act) {
+      // rows of (W + Sigma + delta) dq + J' lam+ (+ g for the edge unknowns)
+      for (int i = c.gl; i < NQ; i += GSZ) {
+        double s = 0.0;
+        for (int t = DMB_HR_START[i]; t < DMB_HR_START[i + 1]; ++t) s += T[STG_HNZ + DMB_HR_IDX[t]] * dq[DMB_HR_COL[t]];
+        for (int t = DMB_JC_START[i]; t < DMB_JC_START[i + 1]; ++t) { const int k = DMB_JC_IDX[t]; s += jz[k] * ln[DMB_J_ROW[k]]; }
+#if NNL > 0
+        for (int t = 0; t < DMB_NNZ_D; ++t) if (DMB_D_COL[t] == i) s += dz[t] * ydv[DMB_D_ROW[t]];
+#endif
+        if (i >= NVP) {
+          const int j = i - NVP;
+          s += (T[STG_SIGY + j] + delta) * dq[i] + T[STG_GY + j];
 #pragma unroll
-    for (int i = 0; i < NY; ++i) {
-      const double r = res[LAM_EDGE(e) + i] + jdq[i];
-      rp[LAM_EDGE(e) + i] = r;
-      nrm_rho = fmax(nrm_rho, fabs(r));
-      rd[EDGE_OFF(e) + i] = hq[NVP + i];
-      nrm_rho = fmax(nrm_rho, fabs(hq[NVP + i]));
-      nrm_rhs = fmax(nrm_rhs, fmax(fabs(eb[EB_GY + i]), fabs(res[LAM_EDGE(e) + i])));
-      nrm_sol = fmax(nrm_sol, fmax(fabs(dq[NVP + i]), fabs(ln[i])));
+          for (int a = 0; a < NX; ++a) if (DMB_XF_SEL[a] == j) s += ln[NY + a];    // + E' lam_C+ on the end-of-interval state
+        }
+        hq[i] = s;
+      }
+      // rows of c + J dq
+      for (int r = c.gl; r < NY; r += GSZ) {
+        double jd = 0.0;
+        for (int k = DMB_JR_START[r]; k < DMB_JR_START[r + 1]; ++k) jd += jz[k] * dq[DMB_J_COL[k]];
+        const double rr = res[LAM_EDGE(e) + r] + jd;
+        rp[LAM_EDGE(e) + r] = rr;
+        nrm_rho = fmax(nrm_rho, fabs(rr));
+        nrm_rhs = fmax(nrm_rhs, fmax(fabs(T[STG_GY + r]), fabs(res[LAM_EDGE(e) + r])));
+        nrm_sol = fmax(nrm_sol, fmax(fabs(dq[NVP + r]), fabs(ln[r])));
+      }
+      const double* dxc = I.dw + NODE_OFF(DMB_EDGE_CHILD[e]);
+      for (int a = c.gl; a < NX; a += GSZ) {
+        const double rr = res[LAM_EDGE(e) + NY + a] + dq[NVP + DMB_XF_SEL[a]] - dxc[a];
+        rp[LAM_EDGE(e) + NY + a] = rr;
+        nrm_rho = fmax(nrm_rho, fabs(rr));
+      }
     }
-#pragma unroll
-    for (int i = 0; i < NVP; ++i) eb[EB_GCON + i] = hq[i];
+    WARP_SYNC();
+    if (act) {
+      for (int i = c.gl; i < NQ; i += GSZ) {
+        if (i < NVP) eb[EB_GCON + i] = hq[i];
+        else { rd[EDGE_OFF(e) + i - NVP] = hq[i]; nrm_rho = fmax(nrm_rho, fabs(hq[i])); }
+      }
+    }
+    WARP_SYNC();
   }
   CTA_SYNC();
   for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {

@@ -178,7 +178,7 @@ DMB_DEV void sens_rhs(const Ctx& c, const Inst& I, int pj) {
 DMB_DEV void sens_solve(const Ctx& c, const Inst& I, int max_refine, double ratio_max, double* tile, double* Qs, DmbShared* S) {
   for (int it = 0; it <= max_refine; ++it) {
     double nr[3];
-    kkt_residual(c, I, I.res, 0.0, 0.0, 0.0, S->red, nr);
+    kkt_residual(c, I, I.res, 0.0, 0.0, 0.0, S->red, nr, tile);
     if (it > 0) {
       const double ratio = nr[0] / (fmin(nr[1], 1e6 * nr[2]) + nr[2] + 1e-300);
       if (!(ratio > ratio_max)) break;

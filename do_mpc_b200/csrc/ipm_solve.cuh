@@ -276,7 +276,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     // ---- iterative refinement of the step (IPOPT: residual_ratio_max 1e-10) ------------------------------------------
     for (int ref_it = 0; ref_it < o.max_refine; ++ref_it) {
       double nr[3];
-      kkt_residual(c, I, I.res, mu, o.kappa_d, delta_w, red, nr);
+      kkt_residual(c, I, I.res, mu, o.kappa_d, delta_w, red, nr, tile);
       const double ratio = nr[0] / (fmin(nr[1], 1e6 * nr[2]) + nr[2] + 1e-300);
 #ifdef DMB_HOSTSIM
       if (dmb_hostsim_verbose) printf("     refine %d: |rho|=%.3e |sol|=%.3e |rhs|=%.3e ratio=%.3e\n", ref_it, nr[0], nr[1], nr[2], ratio);

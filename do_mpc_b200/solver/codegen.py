@@ -131,6 +131,14 @@ def generate(r: Recipe) -> str:
         for c_, k in sorted(row):
             hr_col.append(c_); hr_idx.append(k)
         hr_start.append(len(hr_col))
+    # column-wise (CSC) view of the Jacobian nonzeros: J' lam products with one lane per column
+    jcols = [[] for _ in range(n_q)]
+    for k, c_ in enumerate(jc):
+        jcols[c_].append(k)
+    jc_start, jc_idx = [0], []
+    for col in jcols:
+        jc_idx += col
+        jc_start.append(len(jc_idx))
     dr_start = [0] * (n_nl + 1)
     for r_ in dr: dr_start[r_ + 1] += 1
     for i in range(n_nl): dr_start[i + 1] += dr_start[i]
@@ -243,6 +251,7 @@ def generate(r: Recipe) -> str:
     H.append(_ctab("int", "DMB_H_ROW", hr)); H.append(_ctab("int", "DMB_H_COL", hc))
     H.append(_ctab("int", "DMB_D_ROW", dr)); H.append(_ctab("int", "DMB_D_COL", dcol))
     H.append(_ctab("int", "DMB_JR_START", jr_start)); H.append(_ctab("int", "DMB_DR_START", dr_start))
+    H.append(_ctab("int", "DMB_JC_START", jc_start)); H.append(_ctab("int", "DMB_JC_IDX", jc_idx if jc_idx else [0]))
     H.append(_ctab("int", "DMB_HR_START", hr_start)); H.append(_ctab("int", "DMB_HR_COL", hr_col))
     H.append(_ctab("int", "DMB_HR_IDX", hr_idx))
     H.append(f"#define DMB_NNZ_HR {max(len(hr_col), 1)}")
