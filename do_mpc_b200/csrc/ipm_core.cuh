@@ -182,7 +182,12 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define WV_DS (WV_ST + NEDGE * NNL)
 #define WV_VU (WV_DS + NEDGE * NNL)
 #define WV_END (WV_VU + NEDGE * NNL)
-#define DMB_QS_SIZE (NXI * NVP + NXI + 8)
+#define DMB_QS_WARP (NXI * NVP + NXI + 8)                // Riccati scratch of one warp
+#if defined(DMB_THREADS) && DMB_NSCEN > 1
+#define DMB_QS_SIZE ((DMB_THREADS / 32) * DMB_QS_WARP)    // scenario trees: one scratch per warp, see DMB_TREE_PAR
+#else
+#define DMB_QS_SIZE DMB_QS_WARP
+#endif
 
 #ifdef DMB_HOSTSIM
 #define DMB_CLOCK() 0LL
@@ -852,6 +857,17 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 //        W = P_c [A B]_aug , Q += [A B]_aug' W , Cholesky of Q_uu , K = -Q_uu^{-1} Q_u. , P = Q_xx + Q_xu K (in place).
 // *flag = 1 if a control block is not positive definite (wrong inertia).
 // ---------------------------------------------------------------------------------------------------
+// Scenario trees: the nodes of one stage are independent of each other in both sweeps, so every warp takes some of them and
+// the CTA synchronises once per stage (robust configs: 9 nodes per stage, ~180 nodes — a serial sweep on one warp dominated
+// those problems).  Chains (one node per stage) keep the single-warp sweep without barriers.  Compile-time switch.
+#if DMB_NSCEN > 1 && !defined(DMB_HOSTSIM)
+#define DMB_TREE_PAR 1
+#define DMB_FLAG_OR(flag, bits) atomicOr((flag), (bits))
+#else
+#define DMB_TREE_PAR 0
+#define DMB_FLAG_OR(flag, bits) (*(flag) |= (bits))
+#endif
+
 // lower-triangle index -> (row i >= column j)
 #define NTRI_VP (NVP * (NVP + 1) / 2)
 #define NTRI_XI (NXI * (NXI + 1) / 2)
@@ -953,13 +969,15 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
   CTA_SYNC();
   SUB_START();
   // ---- (2) sweep ----------------------------------------------------------------------------------------------------------
-  if (c.warp == 0) {
-    double* W = Qs;                  // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
-    double* pb = Qs + NXI * NVP;     // NXI       : p_c + P_c[:, x] b
+  const bool par = DMB_TREE_PAR && c.nwarp > 1;
+  {
+    double* W = Qs + (par ? c.warp : 0) * DMB_QS_WARP;   // NXI x NVP : P_c [A B]_aug restricted to the (x, u, eps) columns
+    double* pb = W + NXI * NVP;                          // NXI       : p_c + P_c[:, x] b
     int tvi, tvj, txi, txj;          // this lane's first lower-triangle entry of the two symmetric updates (loop invariant)
     tri_decode(c.lane, tvi, tvj); tri_decode(c.lane, txi, txj);
-    for (int n = NNODE - 1; n >= 0; --n) {
-      if (DMB_NODE_K[n] == NHOR) continue;
+    for (int lvl = NHOR - 1; lvl >= 0; --lvl) {
+     if (par || c.warp == 0)
+     for (int n = DMB_LEVEL_START[lvl + 1] - 1 - (par ? c.warp : 0); n >= DMB_LEVEL_START[lvl]; n -= (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
@@ -1018,7 +1036,7 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
             else L[a * NUT + b] = s * L[b * NUT + b];
           }
         }
-        if (bad && c.lane == 0) *flag |= bad;
+        if (bad && c.lane == 0) DMB_FLAG_OR(flag, bad);
         for (int col = c.lane; col <= NXI; col += DMB_LANES) {
           double rhs[NUT];
 #pragma unroll
@@ -1054,6 +1072,8 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         }
       }
       WARP_SYNC();
+     }
+     if (par) CTA_SYNC();            // the next stage reads the cost-to-go of this one
     }
     SUB_TICK(I, 5);
   }
@@ -1071,10 +1091,13 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
 DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, int refine, double* tile_base) {
   const int gy_off = refine ? EB_GY2 : EB_GY;
   SUB_START();
-  if (c.warp == 0) {
-    for (int n = 0; n < NNODE; ++n) {
+  const bool par = DMB_TREE_PAR && c.nwarp > 1;     // scenario trees: the nodes of a stage roll out on different warps
+  {
+    for (int lvl = 0; lvl <= NHOR; ++lvl) {
+     if (par || c.warp == 0)
+     for (int n = DMB_LEVEL_START[lvl] + (par ? c.warp : 0); n < DMB_LEVEL_START[lvl + 1]; n += (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
-      const int k = DMB_NODE_K[n];
+      const int k = lvl;
       if (n == 0) {
         for (int a = c.lane; a < NXI; a += DMB_LANES) wn[WN_DXI + a] = a < NX ? -res[a] : 0.0;
         WARP_SYNC();
@@ -1103,12 +1126,16 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
         wc[WN_DXI + r] = s;
       }
       WARP_SYNC();
+     }
+     if (par) CTA_SYNC();              // the next stage starts from the states written here
     }
-    const double* w0 = I.node;
-    for (int a = c.lane; a < NX; a += DMB_LANES) {
-      double s = w0[WN_QV + a];
-      for (int t = 0; t < NXI; ++t) s += P_AT(w0, a, t) * w0[WN_DXI + t];
-      I.lamn[a] = -s;
+    if (c.warp == 0) {
+      const double* w0 = I.node;
+      for (int a = c.lane; a < NX; a += DMB_LANES) {
+        double s = w0[WN_QV + a];
+        for (int t = 0; t < NXI; ++t) s += P_AT(w0, a, t) * w0[WN_DXI + t];
+        I.lamn[a] = -s;
+      }
     }
     SUB_TICK(I, 6);
   }

@@ -46,7 +46,7 @@ def _sizes(r: Recipe, src: str, threads: int):
     gsz = 16 if ny <= 16 else 32
     tile = ny * ((ny + 2 * ne) | 1) + nvp * ne + nnz_h + nnz_d + nq + 4 * ny + 2 * nnl
     tiles = (threads // gsz) * tile
-    qs = nxi * nvp + nxi + 8
+    qs = (threads // 32 if r.n_comb ** r.n_robust > 1 else 1) * (nxi * nvp + nxi + 8)      # Riccati scratch (per warp for scenario trees)
     ern = n_edge * (nx * nvp + nx + 2 * nvp * nvp + 2 * nvp) + n_node * (nv * nv + nv + nut * nxi + nut + nxi + 2 * nu + 4 * nu * nu)
     nwi = n_node * nvp + n_edge * ny
     nlam = nx + n_edge * (ny + nx + nnl)

@@ -233,6 +233,12 @@ def generate(r: Recipe) -> str:
     H.append(_ctab("int", "DMB_NODE_K", r.node_k)); H.append(_ctab("int", "DMB_NODE_FIRST_EDGE", r.node_first_edge))
     H.append(_ctab("int", "DMB_NODE_NEDGE", r.node_n_edges)); H.append(_ctab("int", "DMB_NODE_PARENT_EDGE", r.node_parent_edge))
     H.append(_ctab("double", "DMB_NODE_RW", [_dbl(v) for v in node_rw]))
+    # nodes are numbered level by level (k = 0..N): first node of every level, for the level-parallel tree sweeps
+    lvl = [0]
+    for k in range(r.N + 1):
+        lvl.append(lvl[-1] + r.n_scenarios[k])
+    assert lvl[-1] == n_node and all(r.node_k[n] == k for k in range(r.N + 1) for n in range(lvl[k], lvl[k + 1]))
+    H.append(_ctab("int", "DMB_LEVEL_START", lvl))
     H.append(_ctab("int", "DMB_NODE_X_FLAT", r.node_x_flat)); H.append(_ctab("int", "DMB_NODE_U_FLAT", r.node_u_flat))
     H.append(_ctab("int", "DMB_NODE_EPS_FLAT", r.node_eps_flat))
     H.append(_ctab("int", "DMB_EDGE_YX_FLAT", r.edge_yx_flat)); H.append(_ctab("int", "DMB_EDGE_YZ_FLAT", r.edge_yz_flat))
