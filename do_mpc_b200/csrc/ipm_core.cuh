@@ -860,6 +860,11 @@ DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double
 // Scenario trees: the nodes of one stage are independent of each other in both sweeps, so every warp takes some of them and
 // the CTA synchronises once per stage (robust configs: 9 nodes per stage, ~180 nodes — a serial sweep on one warp dominated
 // those problems).  Chains (one node per stage) keep the single-warp sweep without barriers.  Compile-time switch.
+#if DMB_NSCEN > 1
+#define DMB_LVL(l) DMB_LEVEL_START[l]     // first node of stage l
+#else
+#define DMB_LVL(l) (l)                    // chain: node l is stage l
+#endif
 #if DMB_NSCEN > 1 && !defined(DMB_HOSTSIM)
 #define DMB_TREE_PAR 1
 #define DMB_FLAG_OR(flag, bits) atomicOr((flag), (bits))
@@ -977,7 +982,7 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
     tri_decode(c.lane, tvi, tvj); tri_decode(c.lane, txi, txj);
     for (int lvl = NHOR - 1; lvl >= 0; --lvl) {
      if (par || c.warp == 0)
-     for (int n = DMB_LEVEL_START[lvl + 1] - 1 - (par ? c.warp : 0); n >= DMB_LEVEL_START[lvl]; n -= (par ? c.nwarp : 1)) {
+     for (int n = DMB_LVL(lvl + 1) - 1 - (par ? c.warp : 0); n >= DMB_LVL(lvl); n -= (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
@@ -1095,7 +1100,7 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
   {
     for (int lvl = 0; lvl <= NHOR; ++lvl) {
      if (par || c.warp == 0)
-     for (int n = DMB_LEVEL_START[lvl] + (par ? c.warp : 0); n < DMB_LEVEL_START[lvl + 1]; n += (par ? c.nwarp : 1)) {
+     for (int n = DMB_LVL(lvl) + (par ? c.warp : 0); n < DMB_LVL(lvl + 1); n += (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
       const int k = lvl;
       if (n == 0) {

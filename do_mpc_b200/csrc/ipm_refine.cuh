@@ -267,7 +267,7 @@ DMB_PHASE void riccati_vector_t(const Ctx& c, const Inst& I, double delta, doubl
     double* pb = Qs + (par ? c.warp : 0) * DMB_QS_WARP;
     for (int lvl = NHOR - 1; lvl >= 0; --lvl) {
      if (par || c.warp == 0)
-     for (int n = DMB_LEVEL_START[lvl + 1] - 1 - (par ? c.warp : 0); n >= DMB_LEVEL_START[lvl]; n -= (par ? c.nwarp : 1)) {
+     for (int n = DMB_LVL(lvl + 1) - 1 - (par ? c.warp : 0); n >= DMB_LVL(lvl); n -= (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
       for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
         const int e = DMB_NODE_FIRST_EDGE[n] + j;
