@@ -19,6 +19,26 @@ def osc_model(symvar_type="SX"):
     return model
 
 
+def osc_dae_model(symvar_type="SX"):
+    """The same plant as a discrete DAE (reference examples/oscillating_masses_discrete_dae): x+ = z, 0 = z - A x - B u."""
+    model = do_mpc.model.Model("discrete", symvar_type)
+    x = model.set_variable("_x", "x", shape=(4, 1))
+    u = model.set_variable("_u", "u", shape=(1, 1))
+    model.set_expression("cost", sum1(x ** 2))
+    A = np.array([[0.763, 0.460, 0.115, 0.020], [-0.899, 0.763, 0.420, 0.115],
+                  [0.115, 0.020, 0.763, 0.460], [0.420, 0.115, -0.899, 0.763]])
+    B = np.array([[0.014], [0.063], [0.221], [0.367]])
+    x_next = model.set_variable("_z", "x_next", shape=(4, 1))
+    model.set_rhs("x", x_next)
+    model.set_alg("x_next", x_next - A @ x - B @ u)
+    model.setup()
+    return model
+
+
+def osc_dae_mpc(n_horizon=7, setup=True):
+    return osc_mpc(osc_dae_model(), n_horizon=n_horizon, setup=setup)
+
+
 def osc_mpc(model=None, n_horizon=7, setup=True):
     model = model or osc_model()
     mpc = do_mpc.controller.MPC(model)

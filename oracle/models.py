@@ -8,6 +8,7 @@ reference template files configure.  Only the mathematics is restated; nothing i
   cstr_robust()         examples/CSTR/template_model.py:33-100,  template_mpc.py:33-110
   batch_reactor()       examples/batch_reactor/template_model.py:33-75, template_mpc.py:33-86
   oscillating_masses()  examples/oscillating_masses_discrete/template_model.py:33-75, template_mpc.py:33-70
+  oscillating_masses_dae()  examples/oscillating_masses_discrete_dae/template_model.py:33-75, template_mpc.py:33-70
   dip()                 examples/double_inverted_pendulum/template_model.py:33-150, template_mpc.py:33-95
   industrial_poly()     examples/industrial_poly/template_model.py:33-125, template_mpc.py:33-105
 """
@@ -99,6 +100,21 @@ def oscillating_masses(n_horizon=7):
     rhs = [sum(A[i, j] * x[j] for j in range(4)) + B[i] * u[0] for i in range(4)]
     cost = sum(xi ** 2 for xi in x)
     m = ModelDef("discrete", x=x, u=u, rhs=rhs, aux={"cost": cost})
+    mx = np.array([4.0, 10.0, 4.0, 10.0])
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.5, n_robust=0, lterm=cost, mterm=cost, rterm_factor=[1e-4],
+                  x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5])
+
+
+def oscillating_masses_dae(n_horizon=7):
+    """examples/oscillating_masses_discrete_dae/template_model.py:33-75: the same plant written as a discrete DAE —
+    x+ = z, 0 = z - A x - B u (algebraic state z = x_next)."""
+    x = list(sy.symbols("x0:4")); u = [sy.Symbol("u")]; z = list(sy.symbols("z0:4"))
+    A = np.array([[0.763, 0.460, 0.115, 0.020], [-0.899, 0.763, 0.420, 0.115],
+                  [0.115, 0.020, 0.763, 0.460], [0.420, 0.115, -0.899, 0.763]])
+    B = np.array([0.014, 0.063, 0.221, 0.367])
+    alg = [z[i] - sum(A[i, j] * x[j] for j in range(4)) - B[i] * u[0] for i in range(4)]
+    cost = sum(xi ** 2 for xi in x)
+    m = ModelDef("discrete", x=x, u=u, z=z, rhs=list(z), alg=alg, aux={"cost": cost})
     mx = np.array([4.0, 10.0, 4.0, 10.0])
     return MPCDef(m, n_horizon=n_horizon, t_step=0.5, n_robust=0, lterm=cost, mterm=cost, rterm_factor=[1e-4],
                   x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5])

@@ -13,6 +13,7 @@ import oscillating_masses
 EXAMPLES = {
     # name: (factory(setup), golden sizes (n_w, n_g, n_p))
     "oscillatingMasses": (lambda setup=False: oscillating_masses.osc_mpc(setup=setup), (39, 32, 5)),
+    "oscillatingMasses_dae": (lambda setup=False: oscillating_masses.osc_dae_mpc(setup=setup), (67, 60, 5)),
     "batch_reactor": (lambda setup=False: batch_reactor.reactor_mpc(setup=setup), (608, 564, 23)),
     "CSTR": (lambda setup=False: cstr.cstr_robust_mpc(setup=setup), (3564, 3064, 24)),
     "dip": (lambda setup=False: dip.dip_mpc(setup=setup), (4330, 4506, 126)),

@@ -3,7 +3,7 @@
 Run HERE (build container; /root/reference is read-only and absent on the GPU box):
     python tests/golden/make_fixtures.py
 Sources (reference tree):
-  * testing/results/results_{oscillatingMasses,batch_reactor,CSTR,industrial_poly,dip}.pkl — 5 closed-loop steps each,
+  * testing/results/results_{oscillatingMasses,oscillatingMasses_dae,batch_reactor,CSTR,industrial_poly,dip}.pkl — 5 closed-loop steps each,
     fields opt_p_num / _opt_x_num (unscaled primal solution) / _lam_g_num / _u / _x / success (do_mpc/data.py:376-434,
     written by testing/test_*.py).
   * documentation/source/example_gallery/sampling_notebook/my_dataset/{sampling_plan_my_dataset,data_my_dataset_all}.pkl —
@@ -27,10 +27,10 @@ OUT = Path(__file__).resolve().parent
 
 
 def main():
-    for name in ["oscillatingMasses", "batch_reactor", "CSTR", "industrial_poly", "dip"]:
+    for name in ["oscillatingMasses", "oscillatingMasses_dae", "batch_reactor", "CSTR", "industrial_poly", "dip"]:
         m = load_results(REF / "testing" / "results" / f"results_{name}.pkl")["mpc"]
         np.savez_compressed(OUT / f"kkt_{name}.npz", opt_p_num=m["opt_p_num"], opt_x_num=m["_opt_x_num"],
-                            lam_g_num=m["_lam_g_num"], u=m["_u"], x=m["_x"], success=m["success"])
+                            lam_g_num=m["_lam_g_num"], u=m["_u"], x=m["_x"], success=m["success"], **({"z": m["_z"]} if name.endswith("_dae") else {}))
         print(name, m["_opt_x_num"].shape)
     d = REF / "documentation/source/example_gallery/sampling_notebook/my_dataset"
     plan = pickle.load(open(d / "sampling_plan_my_dataset.pkl", "rb"))

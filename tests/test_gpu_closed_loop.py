@@ -10,10 +10,10 @@ from examples_common import EXAMPLES, golden
 pytestmark = pytest.mark.gpu
 
 PLANT = {"CSTR": dict(alpha=1.0, beta=1.0), "batch_reactor": dict(Y_x=0.5, S_in=200.0),
-         "industrial_poly": dict(delH_R=950.0, k_0=7.0), "oscillatingMasses": {}}
+         "industrial_poly": dict(delH_R=950.0, k_0=7.0), "oscillatingMasses": {}, "oscillatingMasses_dae": {}}
 
 
-@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "industrial_poly"])
+@pytest.mark.parametrize("name", ["oscillatingMasses", "oscillatingMasses_dae", "batch_reactor", "CSTR", "industrial_poly"])
 def test_five_closed_loop_steps_match_reference_goldens(name):
     make, _ = EXAMPLES[name]
     mpc = make(setup=True)

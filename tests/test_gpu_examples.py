@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "dip"])
+@pytest.mark.parametrize("name", ["oscillatingMasses", "oscillatingMasses_dae", "batch_reactor", "CSTR", "dip"])
 def test_cold_start_matches_reference_ipopt_on_gpu(name):
     make, sizes = EXAMPLES[name]
     mpc = make(setup=True)

@@ -10,7 +10,7 @@ from examples_common import EXAMPLES, golden, cold_start_inputs
 TOL = 1e-5          # |u0 - u0_ref| <= 1e-5 * u_scaling (north_star tolerance)
 
 
-@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "dip"])
+@pytest.mark.parametrize("name", ["oscillatingMasses", "oscillatingMasses_dae", "batch_reactor", "CSTR", "dip"])
 def test_cold_start_matches_reference_ipopt(name):
     make, sizes = EXAMPLES[name]
     mpc = make(); mpc.prepare_nlp(); r = mpc.recipe

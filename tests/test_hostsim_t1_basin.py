@@ -9,11 +9,11 @@ from examples_common import EXAMPLES, golden
 from oracle import models
 from oracle.nlp import FlatNLP
 
-ORACLE_MODELS = {"oscillatingMasses": models.oscillating_masses, "batch_reactor": models.batch_reactor, "CSTR": models.cstr_robust,
+ORACLE_MODELS = {"oscillatingMasses": models.oscillating_masses, "oscillatingMasses_dae": models.oscillating_masses_dae, "batch_reactor": models.batch_reactor, "CSTR": models.cstr_robust,
                  "dip": models.dip}
 
 
-@pytest.mark.parametrize("name", ["oscillatingMasses", "batch_reactor", "CSTR", "dip"])
+@pytest.mark.parametrize("name", ["oscillatingMasses", "oscillatingMasses_dae", "batch_reactor", "CSTR", "dip"])
 def test_stays_at_the_reference_solution(name):
     make, _ = EXAMPLES[name]
     mpc = make(); mpc.prepare_nlp(); r = mpc.recipe

@@ -10,6 +10,7 @@ from oracle.nlp import FlatNLP
 
 CASES = {
     "oscillatingMasses": (models.oscillating_masses, (39, 32, 5)),
+    "oscillatingMasses_dae": (models.oscillating_masses_dae, (67, 60, 5)),
     "batch_reactor": (models.batch_reactor, (608, 564, 23)),
     "CSTR": (models.cstr_robust, (3564, 3064, 24)),
     "industrial_poly": (models.industrial_poly, (8100, 7210, 31)),

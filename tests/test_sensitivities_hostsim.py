@@ -10,7 +10,7 @@ from oracle import models
 from oracle.nlp import FlatNLP
 from oracle.sens import nlp_sensitivity
 
-ORACLE_MODELS = {"oscillatingMasses": models.oscillating_masses, "batch_reactor": models.batch_reactor,
+ORACLE_MODELS = {"oscillatingMasses": models.oscillating_masses, "oscillatingMasses_dae": models.oscillating_masses_dae, "batch_reactor": models.batch_reactor,
                  "CSTR": models.cstr_robust, "dip": models.dip, "industrial_poly": models.industrial_poly}
 
 
@@ -62,7 +62,7 @@ def test_cstr_matches_finite_differences_of_the_solution_map(cstr_solved):
     assert seen > 0.1          # the compared derivatives are not trivially zero
 
 
-@pytest.mark.parametrize("name,cols", [("oscillatingMasses", None), ("batch_reactor", None), ("CSTR", [0, 2, 5, 12, 22, 23]),
+@pytest.mark.parametrize("name,cols", [("oscillatingMasses", None), ("oscillatingMasses_dae", None), ("batch_reactor", None), ("CSTR", [0, 2, 5, 12, 22, 23]),
                                         ("dip", [0, 4, 6, 27, 106, 107, 110, 125])])
 def test_model_families_match_reference_algorithm(name, cols):
     """discrete / multi-element collocation / scenario tree + soft constraints / DAE + hard nl_cons + tvp:

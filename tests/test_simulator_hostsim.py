@@ -19,6 +19,7 @@ CASES = {
     "industrial_poly": (industrial_poly.poly_model, 50.0 / 3600.0, [950.0, 7.0], None),
     "dip": (dip.dip_model, 0.04, [0.2, 0.2], [0.0]),
     "oscillatingMasses": (oscillating_masses.osc_model, 0.5, None, None),
+    "oscillatingMasses_dae": (oscillating_masses.osc_dae_model, 0.5, None, None),
 }
 
 
