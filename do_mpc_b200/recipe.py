@@ -73,7 +73,8 @@ def build_recipe(mpc) -> Recipe:
     m, st = mpc.model, mpc.settings
     n_x, n_u, n_z, n_tvp, n_pm = m.n_x, m.n_u, m.n_z, m.n_tvp, m.n_p
     N, n_robust, n_comb = st.n_horizon, st.n_robust, mpc.n_combinations
-    if st.open_loop:
+    if st.open_loop and n_comb ** n_robust > 1:
+        # with a single scenario the flag has no effect (one input sequence either way, reference _mpc.py:1113-1117)
         raise NotImplementedError("open_loop=True couples the inputs of all scenarios; not supported by the batched solver")
     if st.nl_cons_single_slack and mpc.n_eps > 0:
         raise NotImplementedError("nl_cons_single_slack couples all stages; not supported by the batched solver")

@@ -23,6 +23,7 @@ VARIANTS = {
     "terminal_bounds": dict(use_terminal_bounds=True),
     "hard_nl_cons_colloc": dict(nl_cons_check_colloc_points=True),
     "soft_nl_cons": dict(),
+    "open_loop_single_scenario": dict(open_loop=True),        # no effect without a scenario tree (reference _mpc.py:1113-1117)
 }
 
 
