@@ -190,11 +190,10 @@ class AMPCSampler:
             self.simulator = Simulator(self.mpc.model)
             self.simulator.set_param(t_step=self.mpc.settings.t_step)
             if self.mpc.model.n_p:
+                # the plant runs with the controller's nominal parameter scenario (first entry of p_fun, reference _ampc_sampler.py:196-203)
                 p_num = self.simulator.get_p_template()
                 p0 = self.mpc.p_fun(0.0)["_p"][0]
-                for k in self.mpc.model._p.keys():
-                    if k != "default":
-                        p_num[k] = p0[k]
+                p_num.master = np.asarray(p0.full() if hasattr(p0, "full") else p0, dtype=float).reshape(-1, 1)
                 self.simulator.set_p_fun(lambda t: p_num)
             if self.mpc.model.n_tvp:
                 tvp_num = self.simulator.get_tvp_template()

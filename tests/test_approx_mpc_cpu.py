@@ -52,3 +52,18 @@ def test_missing_bounds_are_reported():
     a.settings.lbx = [-np.inf, 0.1, 50.0, 50.0]
     with pytest.raises(ValueError, match="lbx"):
         a.setup()
+
+
+def test_closed_loop_sampler_configures_the_plant_with_the_nominal_scenario(monkeypatch):
+    """AMPCSampler.setup() for a model with uncertain parameters (no GPU needed up to the simulator handle)."""
+    import sys
+    import cstr
+    import do_mpc_b200  # noqa: F401
+    from do_mpc_b200.approximateMPC import AMPCSampler
+    Sim = sys.modules["do_mpc_b200.simulator"].Simulator
+    monkeypatch.setattr(Sim, "setup", lambda self: self.flags.__setitem__("setup", True))
+    mpc = cstr.cstr_robust_mpc(setup=False); mpc.prepare_nlp()
+    s = AMPCSampler(mpc)
+    s.settings.n_samples, s.settings.dataset_name, s.settings.closed_loop_flag, s.settings.trajectory_length = 4, "x", True, 2
+    s.setup()
+    assert np.allclose(s.simulator.p_fun(0.0).full().ravel(), [1.0, 1.0])          # alpha, beta of the nominal scenario
