@@ -74,6 +74,8 @@ class TrainerSettings:                  # reference _ampcsettings.py:70-106
     shuffle: bool = True
     learning_rate: float = 1e-3
     save_history: bool = False
+    show_fig: bool = False            # accepted for compatibility; plotting is out of scope
+    save_fig: bool = False
     print_frequency: int = 10
     seed: int = 0
 
