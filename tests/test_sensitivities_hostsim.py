@@ -113,3 +113,28 @@ def test_both_active_set_rules_agree_when_bounds_are_order_one(cstr_solved):
     a, _ = sim.sens(out["x"], out["lam_g"], P, cols=[0, 5], relaxed_rule=0)
     b, _ = sim.sens(out["x"], out["lam_g"], P, cols=[0, 5], relaxed_rule=1)
     assert np.abs(a - b).max() < 1e-7
+
+
+def test_model_parameter_columns_match_finite_differences():
+    """Oracle-independent check of the generated d/dtheta right-hand sides: the uncertain model parameters of the batch reactor
+    (Y_x, S_in of the nominal scenario) against central differences of re-solved problems, first input.  Agreement to a few per
+    cent only: inputs that sit 1e-6..1e-3 from a bound further down the horizon are 'inactive' for the reference's primal test but
+    held by the barrier in the re-solves (see the CSTR test above); the exact comparison is the one against oracle/sens.py."""
+    name, cols = "batch_reactor", [4, 5]
+    make, _ = EXAMPLES[name]
+    mpc = make(); mpc.prepare_nlp(); r = mpc.recipe
+    g = golden(name)
+    sim = HostSim(mpc, name); sim.o.max_iter = 500
+    P, x0s, u0s, z0s = cold_start_inputs(r, g)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    assert out["status"][0] == 0
+    dx, sst = sim.sens(out["x"], out["lam_g"], P, cols=cols)
+    iu = np.asarray(mpc._opt_x.f_index(("_u", 0, 0)), dtype=int)
+    for jc, j in enumerate(cols):
+        h = 1e-4 * max(1.0, abs(P[0, j]))
+        Pp = P.copy(); Pp[0, j] += h; Pm = P.copy(); Pm[0, j] -= h
+        op = sim.solve(Pp, x_init=out["x"]); om = sim.solve(Pm, x_init=out["x"])
+        assert op["status"][0] == 0 and om["status"][0] == 0
+        fd = (op["x"][0] - om["x"][0]) / (2 * h)
+        scale = np.abs(fd[iu]).max()
+        assert scale > 1e-5 and np.abs(dx[0, jc][iu] - fd[iu]).max() < 5e-2 * scale, (j, dx[0, jc][iu], fd[iu])
