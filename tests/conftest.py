@@ -38,8 +38,10 @@ def build_hostsim(recipe, tag):
     if not so.exists():
         d.mkdir(parents=True, exist_ok=True)
         (d / "problem_gen.h").write_text(src)
+        tmp = d / f"hostsim.{os.getpid()}.tmp"
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-I{d}", f"-I{csrc}",
-                        str(ROOT / "tests" / "hostsim" / "hostsim.cpp"), "-o", str(so)], check=True)
+                        str(ROOT / "tests" / "hostsim" / "hostsim.cpp"), "-o", str(tmp)], check=True)
+        os.replace(tmp, so)                          # atomic: concurrent test processes may build the same emulation
     return ctypes.CDLL(str(so))
 
 

@@ -39,6 +39,12 @@ def test_sharded_solve_equals_single_process(dataset):
     n_total = 37                                  # ragged: 19 + 18
     assert shard_bounds(n_total, 2, 0) == (0, 19) and shard_bounds(n_total, 2, 1) == (19, 37)
     assert shard_bounds(7, 3, 2) == (5, 7) and sum(b - a for a, b in (shard_bounds(10, 4, r) for r in range(4))) == 10
+    # build the CPU emulation once here so that the two ranks only load it
+    sys.path.insert(0, str(ROOT / "examples"))
+    import cstr
+    from conftest import HostSim
+    m = cstr.cstr_nominal_mpc(setup=False); m.prepare_nlp()
+    HostSim(m, "cstr_nominal")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
