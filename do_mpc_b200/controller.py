@@ -450,13 +450,16 @@ class MPC:
         return u0
 
     # ---- batched entry point ---------------------------------------------------------------------------------------------------------------------
-    def make_step_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None, return_full=False):
+    def make_step_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None, return_full=False, warm_from=None):
         """Solve B independent controller steps at once (cold start per instance, as the reference's sampler
         does one by one: reset_history(); x0=..; u0=..; set_initial_guess(); make_step(x0),
         do_mpc/approximateMPC/_ampc_sampler.py:312-320).
 
         X0: (B, n_x); U_prev: (B, n_u) (default: current u0); returns dict with 'u0' (B, n_u), 'success' (B,),
         'iter_count' (B,), 'status' (B,) and, if return_full, the primal/dual solution arrays.
+        warm_from: the dict returned by a previous call with return_full=True — its primal solution becomes the initial guess
+        (what make_step() does from one sampling instant to the next, optimizer.py:741-742) and, with
+        nlpsol_opts['ipopt.warm_start_init_point']='yes', its multipliers are taken over as well.
         """
         assert self.flags["setup"] == True, "MPC was not setup yet. Please call MPC.setup()."
         X0 = np.ascontiguousarray(np.asarray(X0, dtype=float).reshape(-1, self.model.n_x))
@@ -476,9 +479,14 @@ class MPC:
                 else np.asarray(p, dtype=float)
             P_[:, r.p_p:r.p_p + r.n_comb * r.n_pm] = pv.reshape(-1, r.n_comb * r.n_pm)
         Zs = None if not r.n_z else (np.tile(self._z0.full().ravel(), (B, 1)) if Z0 is None else np.asarray(Z0, dtype=float))
+        ws = {}
+        if warm_from is not None:
+            if "x" not in warm_from:
+                raise ValueError("warm_from must come from make_step_batch(..., return_full=True)")
+            ws = dict(x_init=warm_from["x"], lam_g0=warm_from.get("lam_g"), lam_x0=warm_from.get("lam_x"))
         out = self.S.solve_batch(P_, X0 / r.x_scaling, U_prev / r.u_scaling,
                                  None if Zs is None else Zs / r.z_scaling,
-                                 self._lb_opt_x.full().ravel(), self._ub_opt_x.full().ravel(), return_full=return_full)
+                                 self._lb_opt_x.full().ravel(), self._ub_opt_x.full().ravel(), return_full=return_full, **ws)
         out["u0"] = out["u0_scaled"] * r.u_scaling
         out["p"] = P_
         return out
