@@ -110,12 +110,12 @@ class MPC:
                 print(f"Warning: Key {k} does not exist for MPC.")
 
     # ---- bounds / scaling ----------------------------------------------------------------------------------------
-    def _bstruct(self, ind, terminal=False):
+    def _bstruct(self, ind):
         assert isinstance(ind, tuple) and len(ind) >= 3, "Power index must include bound_type, var_type, var_name (as a tuple)."
         bt, vt = ind[0], ind[1]
         assert bt in ("lower", "upper"), f"Invalid power index {bt} for bound_type. Must be from (lower, upper)."
         assert vt in ("_x", "_u", "_z"), f"Invalid power index {vt} for var_type. Must be from (_x, _u, _z)."
-        name = f"{vt}{'_terminal' if terminal else ''}_{'lb' if bt == 'lower' else 'ub'}"
+        name = f"{vt}_{'lb' if bt == 'lower' else 'ub'}"
         s = getattr(self, name)
         assert ind[2] in s.keys(), f"Calling .bounds with {ind} is not valid. Possible keys are {s.keys()}."
         return s, ind[2:]
@@ -128,11 +128,25 @@ class MPC:
         if self.flags["prepare_nlp"]:
             self._update_bounds()
 
+    def _tbstruct(self, ind):
+        """terminal_bounds index = (bound_type, var_name[, ...]) as in the reference (_mpc.py:408-478: always the states);
+        the 3-tuple form with an explicit '_x' var_type is tolerated."""
+        assert isinstance(ind, tuple), "Power index must include bound_type, var_name (as a tuple)."
+        assert len(ind) >= 2, "Power index must include bound_type, var_type, var_name (as a tuple)."
+        bt = ind[0]
+        assert bt in ("lower", "upper"), f"Invalid power index {bt} for bound_type. Must be from (lower, upper)."
+        name = ind[1:]
+        if name[0] == "_x" and len(name) >= 2:
+            name = name[1:]
+        s = self._x_terminal_lb if bt == "lower" else self._x_terminal_ub
+        assert name[0] in s.keys(), f"Calling .bounds with {ind} is not valid. Possible keys are {s.keys()}."
+        return s, name
+
     def _get_tbounds(self, ind):
-        s, k = self._bstruct(ind, True); return s[k]
+        s, k = self._tbstruct(ind); return s[k]
 
     def _set_tbounds(self, ind, val):
-        s, k = self._bstruct(ind, True); s[k] = val
+        s, k = self._tbstruct(ind); s[k] = val
         if self.flags["prepare_nlp"]:
             self._update_bounds()
 
@@ -324,6 +338,7 @@ class MPC:
     def create_nlp(self) -> None:
         from .solver import BatchedNlpSolver
         self.S = BatchedNlpSolver(self.recipe, self.settings.nlpsol_opts)
+        self.S.bounds_source = lambda: (self._lb_opt_x.full().ravel(), self._ub_opt_x.full().ravel())
         meta = {k: getattr(self.settings, k) for k in asdict(self.settings).keys()}
         self.data.set_meta(**meta)
         self.data.prepare(self)
@@ -449,19 +464,11 @@ class MPC:
         if self.model.n_z: self._z0 = self.model._z(z0)
         return u0
 
-    # ---- batched entry point ---------------------------------------------------------------------------------------------------------------------
-    def make_step_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None, return_full=False, warm_from=None):
-        """Solve B independent controller steps at once (cold start per instance, as the reference's sampler
-        does one by one: reset_history(); x0=..; u0=..; set_initial_guess(); make_step(x0),
-        do_mpc/approximateMPC/_ampc_sampler.py:312-320).
-
-        X0: (B, n_x); U_prev: (B, n_u) (default: current u0); returns dict with 'u0' (B, n_u), 'success' (B,),
-        'iter_count' (B,), 'status' (B,) and, if return_full, the primal/dual solution arrays.
-        warm_from: the dict returned by a previous call with return_full=True — its primal solution becomes the initial guess
-        (what make_step() does from one sampling instant to the next, optimizer.py:741-742) and, with
-        nlpsol_opts['ipopt.warm_start_init_point']='yes', its multipliers are taken over as well.
-        """
-        assert self.flags["setup"] == True, "MPC was not setup yet. Please call MPC.setup()."
+    def pack_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None):
+        """Inputs of B independent controller steps in the solver's layout: opt_p rows P [B, n_p] (reference order
+        [_x0 | _tvp(N+1) | _p(n_comb) | _u_prev], _mpc.py:1160-1165) and the scaled broadcast initial guess (x0s, u0s, z0s) that
+        set_initial_guess() would produce per instance (_mpc.py:969-971).  tvp / p default to tvp_fun(t0) / p_fun(t0)."""
+        assert self.flags["prepare_nlp"] == True, "MPC was not prepared yet. Please call MPC.setup() or MPC.prepare_nlp()."
         X0 = np.ascontiguousarray(np.asarray(X0, dtype=float).reshape(-1, self.model.n_x))
         B = X0.shape[0]
         U_prev = np.tile(self._u0.full().ravel(), (B, 1)) if U_prev is None else \
@@ -478,14 +485,30 @@ class MPC:
             pv = np.concatenate([np.asarray(v.full()).ravel() for v in self.p_fun(self._t0)["_p"]]) if p is None \
                 else np.asarray(p, dtype=float)
             P_[:, r.p_p:r.p_p + r.n_comb * r.n_pm] = pv.reshape(-1, r.n_comb * r.n_pm)
-        Zs = None if not r.n_z else (np.tile(self._z0.full().ravel(), (B, 1)) if Z0 is None else np.asarray(Z0, dtype=float))
+        Zs = None if not r.n_z else (np.tile(self._z0.full().ravel(), (B, 1)) if Z0 is None else np.asarray(Z0, dtype=float).reshape(B, r.n_z))
+        return P_, X0 / r.x_scaling, U_prev / r.u_scaling, None if Zs is None else Zs / r.z_scaling
+
+    # ---- batched entry point ---------------------------------------------------------------------------------------------------------------------
+    def make_step_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None, return_full=False, warm_from=None):
+        """Solve B independent controller steps at once (cold start per instance, as the reference's sampler
+        does one by one: reset_history(); x0=..; u0=..; set_initial_guess(); make_step(x0),
+        do_mpc/approximateMPC/_ampc_sampler.py:312-320).
+
+        X0: (B, n_x); U_prev: (B, n_u) (default: current u0); returns dict with 'u0' (B, n_u), 'success' (B,),
+        'iter_count' (B,), 'status' (B,) and, if return_full, the primal/dual solution arrays.
+        warm_from: the dict returned by a previous call with return_full=True — its primal solution becomes the initial guess
+        (what make_step() does from one sampling instant to the next, optimizer.py:741-742) and, with
+        nlpsol_opts['ipopt.warm_start_init_point']='yes', its multipliers are taken over as well.
+        """
+        assert self.flags["setup"] == True, "MPC was not setup yet. Please call MPC.setup()."
+        P_, x0s, u0s, z0s = self.pack_batch(X0, U_prev, Z0, tvp, p)
+        r = self.recipe
         ws = {}
         if warm_from is not None:
             if "x" not in warm_from:
                 raise ValueError("warm_from must come from make_step_batch(..., return_full=True)")
             ws = dict(x_init=warm_from["x"], lam_g0=warm_from.get("lam_g"), lam_x0=warm_from.get("lam_x"))
-        out = self.S.solve_batch(P_, X0 / r.x_scaling, U_prev / r.u_scaling,
-                                 None if Zs is None else Zs / r.z_scaling,
+        out = self.S.solve_batch(P_, x0s, u0s, z0s,
                                  self._lb_opt_x.full().ravel(), self._ub_opt_x.full().ravel(), return_full=return_full, **ws)
         out["u0"] = out["u0_scaled"] * r.u_scaling
         out["p"] = P_

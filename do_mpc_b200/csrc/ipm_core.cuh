@@ -120,12 +120,7 @@ enum DmbStatus {
 #define STG_INVD (STG_GOBJ + NQ)
 #define STG_PERM (STG_INVD + NY)                       // perm[m] = original row of the m-th pivot (as doubles)
 #define STG_DQ STG_GOBJ                                // recovery phase re-uses that space: dq (NQ), r (NY), jd (NNL)
-#ifdef DMB_USE_REG_LU
-#define STG_PB (STG_PERM + NY)                         // double-buffered published pivot row (2 x TILE_NC)
-#define TILE_SZ (STG_PB + 2 * TILE_NC)
-#else
 #define TILE_SZ (STG_PERM + NY)
-#endif
 static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY >= NNL");
 
 // per-edge reduced data kept in shared memory (inputs of the Riccati sweep)
@@ -181,7 +176,9 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define WV_ST (WV_S + NEDGE * NNL)
 #define WV_DS (WV_ST + NEDGE * NNL)
 #define WV_VU (WV_DS + NEDGE * NNL)
-#define WV_END (WV_VU + NEDGE * NNL)
+#define WV_S2 (WV_VU + NEDGE * NNL)                       // second-order-correction trial slacks / restoration slack iterate
+#define WV_SOC (WV_S2 + NEDGE * NNL)                      // residual of a second-order-correction trial point (NLAM)
+#define WV_END (WV_SOC + NLAM)
 #define DMB_QS_WARP (NXI * NVP + NXI + 8)                // Riccati scratch of one warp
 #if defined(DMB_THREADS) && DMB_NSCEN > 1
 #define DMB_QS_SIZE ((DMB_THREADS / 32) * DMB_QS_WARP)    // scenario trees: one scratch per warp, see DMB_TREE_PAR
@@ -204,16 +201,29 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #endif
 struct Inst {
   long long* sub;      // optional fine-grained cycle counters (thread 0 only), see SUB_TICK
-  double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *lamr, *res, *rest, *dc, *s, *st, *ds, *vU;
+  double *w, *wt, *dw, *zL, *zU, *gl, *go, *lam, *lamn, *lamr, *res, *rest, *dc, *s, *st, *ds, *vU, *s2, *soc;
   double *er, *node, *eb;
   const double *p, *lb, *ub;
   double df, relax_fac, relax_max;
+  // feasibility restoration (ipm_solve.cuh): resto != 0 switches the barrier terms of every primal variable to those of the
+  // restoration problem (see resto_terms), zeta = sqrt(mu); the reference point of its proximal term is kept in go / s2
+  double zeta;
+  int resto;
 };
+// restoration problem  min zeta/2 |D_R (v - v_R)|^2 - mu log(v - lo) - mu log(hi - v), D_R = 1/max(1,|v_R|): diagonal Hessian
+// entry and gradient of one variable (primal barrier: no multipliers involved)
+DMB_DEV void resto_terms(double zeta, double mu, double v, double vref, double lo, double hi, bool hl, bool hu, double& sig, double& gb) {
+  const double dr = 1.0 / fmax(1.0, fabs(vref));
+  sig = zeta * dr * dr; gb = sig * (v - vref);
+  if (hl) { const double rs = 1.0 / (v - lo); sig += mu * rs * rs; gb -= mu * rs; }
+  if (hu) { const double rs = 1.0 / (hi - v); sig += mu * rs * rs; gb += mu * rs; }
+}
 DMB_DEV void bind_vectors(Inst& I, double* vec) {
   I.w = vec + WV_W; I.wt = vec + WV_WT; I.dw = vec + WV_DW; I.zL = vec + WV_ZL; I.zU = vec + WV_ZU;
   I.gl = vec + WV_GL; I.go = vec + WV_GO;
   I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.lamr = vec + WV_LAMR; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
-  I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU;
+  I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU; I.s2 = vec + WV_S2; I.soc = vec + WV_SOC;
+  I.zeta = 0.0; I.resto = 0;
 }
 DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + k * DMB_NTVP; }
 
@@ -421,7 +431,7 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
         const double* eb = I.eb + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ;
         go += eb[EB_GOBJ + i]; gc += eb[EB_GCON + i];
       }
-    } else if (i >= NX) { I.gl[idx] = 0.0; I.go[idx] = 0.0; continue; }
+    } else if (i >= NX) { I.gl[idx] = 0.0; if (!I.resto) I.go[idx] = 0.0; continue; }
     if (i < NX) {
       const int pe = DMB_NODE_PARENT_EDGE[n];
       if (pe >= 0) {
@@ -442,13 +452,15 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
         go += I.node[(size_t)cn * WN_NODE + WN_RG + NU + iu];
       }
     }
-    I.go[idx] = go; I.gl[idx] = go + gc;
+    if (!I.resto) I.go[idx] = go;            // restoration: go holds the reference point of the proximal term
+    I.gl[idx] = go + gc;
   }
   for (int idx = c.tid; idx < NEDGE * NY; idx += c.nthr) {
     const int e = idx / NY, i = idx - e * NY;
     const double* eb = I.eb + (size_t)e * EB_SZ;
     const double go = eb[EB_GOBJ + NVP + i];
-    I.go[NNODE * NVP + idx] = go; I.gl[NNODE * NVP + idx] = go + eb[EB_GCON + NVP + i];
+    if (!I.resto) I.go[NNODE * NVP + idx] = go;
+    I.gl[NNODE * NVP + idx] = go + eb[EB_GCON + NVP + i];
   }
   CTA_SYNC();
 }
@@ -460,7 +472,7 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
 // blocks for the Riccati sweep.  `res` supplies the right-hand side (ignored in ls_mode: zero).
 // ls_mode = least-squares multiplier estimate: Hessian := identity, gradient := grad f - zL + zU.
 // ---------------------------------------------------------------------------------------------------
-DMB_PHASE void factor_edges_smem(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
+DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
                                double* tile_base, int* fail) {
   double* T = tile_base + (size_t)c.grp * TILE_SZ;
   SUB_START();
@@ -495,7 +507,8 @@ DMB_PHASE void factor_edges_smem(const Ctx& c, const Inst& I, const double* res,
           sig = 1.0;
           if (hl) gb -= I.zL[i];
           if (hu) gb += I.zU[i];
-        } else {
+        } else if (I.resto) resto_terms(I.zeta, mu, wy, I.go[i], lo, hi, hl, hu, sig, gb);
+        else {
           if (hl) { const double rs = 1.0 / (wy - lo); sig += I.zL[i] * rs; gb -= mu * rs; if (!hu) gb += kappa_d * mu; }
           if (hu) { const double rs = 1.0 / (hi - wy); sig += I.zU[i] * rs; gb += mu * rs; if (!hl) gb -= kappa_d * mu; }
         }
@@ -507,9 +520,14 @@ DMB_PHASE void factor_edges_smem(const Ctx& c, const Inst& I, const double* res,
 #if NNL > 0
       for (int i = c.gl; i < NNL; i += GSZ) {
         const double sl = nl_ub_relaxed(I, e, i) - I.s[e * NNL + i];
-        const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
+        double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
         // r_d = Sigma_s (d - s) + grad_s phi ; grad_s phi = mu/sl - kappa_d*mu (upper bound only)
-        const double rd = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
+        double rd = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
+        if (I.resto && !ls_mode) {
+          double gs;
+          resto_terms(I.zeta, mu, I.s[e * NNL + i], I.s2[e * NNL + i], 0.0, nl_ub_relaxed(I, e, i), false, true, sig, gs);
+          rd = sig * res[LAM_EDGE(e) + NY + NX + i] + gs;
+        }
         T[STG_SIGS + i] = sig; T[STG_RD + i] = rd;
         eb[EB_SIGS + i] = sig; eb[EB_RD + i] = rd;
       }
@@ -640,214 +658,6 @@ DMB_PHASE void factor_edges_smem(const Ctx& c, const Inst& I, const double* res,
   CTA_SYNC();
 }
 
-#if !defined(DMB_HOSTSIM) && (DMB_NY <= 32) && defined(DMB_USE_REG_LU)
-#define DMB_HAVE_REG_LU 1
-// ---------------------------------------------------------------------------------------------------
-// Register-resident variant of the factor phase (device only, one row per lane): every lane keeps its row of
-// [G_y | G_vp | rhs] in registers; per pivot step only the pivot row is published through shared memory.
-// Written after ncu capture r1b / the cycle counters showed the shared-memory version spending ~1.5k cycles per
-// pivot step in store->load dependent chains.  Same numerics (partial pivoting, reciprocal pivots).
-// ---------------------------------------------------------------------------------------------------
-DMB_PHASE void factor_edges_reg(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
-                              double* tile_base, int* fail) {
-  double* T = tile_base + (size_t)c.grp * TILE_SZ;
-  SUB_START();
-  for (int e0 = 0; e0 < NEDGE; e0 += c.ngrp) {
-    const int e = e0 + c.grp;
-    const bool act = e < NEDGE;
-    double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
-    double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
-    const double* dc = I.dc + LAM_EDGE(act ? e : 0);
-    if (act) {
-      for (int i = c.gl; i < NY * TILE_LD; i += GSZ) T[i] = 0.0;
-      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
-      DMB_COPY_BATCH(NQ, c.gl, GSZ, eb[EB_GOBJ + idx], T[STG_GOBJ + idx] = val);
-#if NNL > 0
-      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
-#endif
-    }
-    WARP_SYNC();
-    if (act) {
-      DMB_COPY_BATCH(DMB_NNZ_J, c.gl, GSZ, eb[EB_JNZ + idx],
-                     const int r = DMB_J_ROW[idx]; const int cq = DMB_J_COL[idx]; T[r * TILE_LD + (cq >= NVP ? cq - NVP : NY + cq)] = dc[r] * val);
-      for (int r = c.gl; r < NY; r += GSZ) {
-        T[r * TILE_LD + NY + NVP] = ls_mode ? 0.0 : -res[LAM_EDGE(e) + r];
-        const int i = EDGE_OFF(e) + r;
-        const double lo = I.lb[i], hi = I.ub[i], wy = I.w[i];
-        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
-        double sig = 0.0, gb = 0.0;
-        if (ls_mode) {
-          sig = 1.0;
-          if (hl) gb -= I.zL[i];
-          if (hu) gb += I.zU[i];
-        } else {
-          if (hl) { const double rs = 1.0 / (wy - lo); sig += I.zL[i] * rs; gb -= mu * rs; if (!hu) gb += kappa_d * mu; }
-          if (hu) { const double rs = 1.0 / (hi - wy); sig += I.zU[i] * rs; gb += mu * rs; if (!hl) gb -= kappa_d * mu; }
-        }
-        T[STG_SIGY + r] = sig;
-        T[STG_GY + r] = T[STG_GOBJ + NVP + r] + gb;
-        eb[EB_SIGY + r] = sig;
-        eb[EB_GY + r] = T[STG_GY + r];
-      }
-#if NNL > 0
-      for (int i = c.gl; i < NNL; i += GSZ) {
-        const double sl = nl_ub_relaxed(I, e, i) - I.s[e * NNL + i];
-        const double sig = ls_mode ? 1.0 : I.vU[e * NNL + i] / sl;
-        const double rd = ls_mode ? I.vU[e * NNL + i] : sig * res[LAM_EDGE(e) + NY + NX + i] + mu / sl - kappa_d * mu;
-        T[STG_SIGS + i] = sig; T[STG_RD + i] = rd;
-        eb[EB_SIGS + i] = sig; eb[EB_RD + i] = rd;
-      }
-#endif
-    }
-    WARP_SYNC();
-    SUB_TICK(I, 0);
-    // ---- LU, rows in registers ------------------------------------------------------------------------------------------
-    const bool has_row = act && c.gl < NY;
-    double a[TILE_NC];
-#pragma unroll
-    for (int cc = 0; cc < TILE_NC; ++cc) a[cc] = has_row ? T[c.gl * TILE_LD + cc] : 0.0;
-    int rank = has_row ? -1 : NY;
-    WARP_SYNC();
-#pragma unroll
-    for (int k = 0; k < NY; ++k) {
-      const int pr = group_argmax(c, rank == -1 ? fabs(a[k]) : -1.0, rank == -1 ? c.gl : -1);
-      double* pbk = T + STG_PB + (k & 1) * TILE_NC;
-      if (act && c.gl == pr) {
-        rank = k;
-        T[STG_PERM + k] = (double)c.gl;
-#pragma unroll
-        for (int cc = k; cc < TILE_NC; ++cc) pbk[cc] = a[cc];
-      }
-      WARP_SYNC();
-      if (act) {
-        const double pv = pbk[k];
-        if (!(fabs(pv) > 1e-300)) *fail = 1;
-        const double inv = 1.0 / pv;
-        if (rank == -1) {
-          const double l = a[k] * inv;
-          a[k] = l;
-#pragma unroll
-          for (int cc = k + 1; cc < TILE_NC; ++cc) a[cc] -= l * pbk[cc];
-        }
-        if (c.gl == 0) T[STG_INVD + k] = inv;
-      }
-    }
-    // rows back to the tile in pivot order
-    if (has_row) {
-#pragma unroll
-      for (int cc = 0; cc < TILE_NC; ++cc) T[rank * TILE_LD + cc] = a[cc];
-    }
-    WARP_SYNC();
-    SUB_TICK(I, 1);
-    // ---- back substitution: one lane per right-hand side, solution column in registers ----------------------------
-    const int j = c.gl;
-    const bool has_col = act && j < NE;
-    double x[NY];
-    if (has_col) {
-#pragma unroll
-      for (int k = NY - 1; k >= 0; --k) {
-        double sx = T[k * TILE_LD + NY + j];
-#pragma unroll
-        for (int cc = k + 1; cc < NY; ++cc) sx -= T[k * TILE_LD + cc] * x[cc];
-        x[k] = sx * T[STG_INVD + k];
-      }
-      if (j < NVP) {
-#pragma unroll
-        for (int k = 0; k < NY; ++k) x[k] = -x[k];
-      }
-    }
-    WARP_SYNC();          // everybody finished reading the eliminated right-hand sides
-    if (has_col) {
-#pragma unroll
-      for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = x[k];
-    }
-    if (act) {
-      for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
-      for (int idx = c.gl; idx < NY * NY; idx += GSZ) {
-        const int r = idx / NY, cc = idx - r * NY;
-        eb[EB_LU + idx] = r == cc ? T[STG_INVD + r] : T[r * TILE_LD + cc];
-      }
-    }
-    WARP_SYNC();
-    SUB_TICK(I, 2);
-    // ---- z = H_e t with t = column j of [I; Yext] (generated straight-line), then the reduced column ---------------
-    double z[NQ];
-    if (has_col) {
-      double t[NQ];
-#pragma unroll
-      for (int i = 0; i < NVP; ++i) t[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < NY; ++k) t[NVP + k] = x[k];
-      gen_hmul(T + STG_HNZ, t, z);
-#pragma unroll
-      for (int k = 0; k < NY; ++k) z[NVP + k] += T[STG_SIGY + k] * x[k];
-      if (j == NVP) {           // right-hand-side column: add the gradient
-#pragma unroll
-        for (int i = 0; i < NVP; ++i) z[i] += T[STG_GOBJ + i];
-#pragma unroll
-        for (int k = 0; k < NY; ++k) z[NVP + k] += T[STG_GY + k];
-      }
-    }
-    if (act) {
-      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; eb[EB_Y + idx] = T[r * TILE_LD + NY + idx - r * NE]; }
-    }
-    SUB_TICK(I, 3);
-    if (has_col) {
-#pragma unroll
-      for (int b = 0; b < NVP; ++b) {
-        double hh = z[b], yty = 0.0;
-#pragma unroll
-        for (int k = 0; k < NY; ++k) {
-          const double ykb = T[k * TILE_LD + NY + b];
-          hh += ykb * z[NVP + k];
-          yty += ykb * x[k];
-        }
-        if (j < NVP) { er[ER_HH + b * NVP + j] = hh; er[ER_YTY + b * NVP + j] = yty; }
-        else { er[ER_GH + b] = hh; er[ER_YTY0 + b] = yty; }
-      }
-    }
-    if (act) {
-      for (int idx = c.gl; idx < NX * NVP; idx += GSZ) { const int r = idx / NVP; er[ER_AB + idx] = T[DMB_XF_SEL[r] * TILE_LD + NY + idx - r * NVP]; }
-      for (int i = c.gl; i < NX; i += GSZ)
-        er[ER_B + i] = T[DMB_XF_SEL[i] * TILE_LD + NY + NVP] + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + i]);
-    }
-    WARP_SYNC();
-    SUB_TICK(I, 4);
-#if NNL > 0
-    if (act) {
-      for (int i = 0; i < NNL; ++i) {
-        double* tv = T + STG_DQ;
-        for (int aa = c.gl; aa < NE; aa += GSZ) {
-          double sd = 0.0;
-          for (int tt = DMB_DR_START[i]; tt < DMB_DR_START[i + 1]; ++tt) {
-            const int cq = DMB_D_COL[tt];
-            if (cq >= NVP) sd += T[STG_DNZ + tt] * T[(cq - NVP) * TILE_LD + NY + aa];
-            else if (cq == aa) sd += T[STG_DNZ + tt];
-          }
-          tv[aa] = sd;
-        }
-        WARP_SYNC();
-        const double sig = T[STG_SIGS + i], rd = T[STG_RD + i] + sig * tv[NVP];
-        for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) er[ER_HH + idx] += sig * tv[idx / NVP] * tv[idx % NVP];
-        for (int aa = c.gl; aa < NVP; aa += GSZ) er[ER_GH + aa] += tv[aa] * rd;
-        WARP_SYNC();
-      }
-    }
-    WARP_SYNC();
-#endif
-  }
-  CTA_SYNC();
-}
-#endif
-
-DMB_DEV void factor_edges(const Ctx& c, const Inst& I, const double* res, double mu, double kappa_d, int ls_mode,
-                          double* tile_base, int* fail) {
-#ifdef DMB_HAVE_REG_LU
-  factor_edges_reg(c, I, res, mu, kappa_d, ls_mode, tile_base, fail);
-#else
-  factor_edges_smem(c, I, res, mu, kappa_d, ls_mode, tile_base, fail);
-#endif
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Riccati sweep over the scenario tree.  v-space ordering: (x [NX], u_prev [NU], u [NU], eps [NEPS]).
@@ -942,7 +752,8 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         sig = 1.0;
         if (hl) gb -= I.zL[gi];
         if (hu) gb += I.zU[gi];
-      } else {
+      } else if (I.resto) { resto_terms(I.zeta, mu, wx, I.go[gi], lo, hi, hl, hu, sig, gb); sig += delta; }
+      else {
         if (hl) { const double sl = wx - lo; sig += I.zL[gi] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
         if (hu) { const double su = hi - wx; sig += I.zU[gi] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
       }
@@ -1161,7 +972,8 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
 #if NNL > 0
       for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
-      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? 0.0 : eb[EB_RD + i]; }
+      // re-solve with a new right-hand side: r_d = Sigma_s rp_d (zero in a refinement solve, where the condensed rows are exact)
+      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? eb[EB_SIGS + i] * res[LAM_EDGE(e) + NY + NX + i] : eb[EB_RD + i]; }
 #endif
       const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];

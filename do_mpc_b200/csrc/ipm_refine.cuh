@@ -209,7 +209,7 @@ DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
         for (int i = 0; i < NY; ++i) z[NVP + i] += T[STG_SIGY + i] * bv[i];
 #if NNL > 0
         for (int i = 0; i < NNL; ++i) {
-          double jd = 0.0;
+          double jd = rp[LAM_EDGE(e) + NY + NX + i];          // right-hand side of the condensed row (0 in a refinement solve)
           for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) if (DMB_D_COL[t] >= NVP) jd += eb[EB_DNZ + t] * bv[DMB_D_COL[t] - NVP];
           for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) z[DMB_D_COL[t]] += eb[EB_DNZ + t] * eb[EB_SIGS + i] * jd;
         }

@@ -80,9 +80,93 @@ DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, dou
   *s_c = fmax(s_max, SZ / fmax(NZ, 1.0)) / s_max;
 }
 
+// ---- cold-path helpers: ONE out-of-line copy each, shared by the starting point, the second-order correction and the
+// restoration phase (the hot loop keeps its own inlined copies; DESIGN.md §4 on the instruction footprint) ------------------
+#ifdef DMB_HOSTSIM
+#define DMB_COLD static
+#else
+#define DMB_COLD __device__ __noinline__
+#endif
+DMB_COLD void eval_point_cold(const Ctx& c, const Inst& I, const double* w, const double* s, double* res, double* scratch,
+                              double* f_out, double* theta_out, double* infpr_out) {
+  eval_point(c, I, w, s, res, scratch, f_out, theta_out, infpr_out);
+}
+// K [dw; lam+; ds] = -[rd; rp] with the factors of the current iteration: rd = I.gl, rp = I.rest  ->  I.dw, I.lamn, I.ds
+#ifdef DMB_RESOLVE_INLINE
+DMB_DEV
+#else
+DMB_COLD
+#endif
+void resolve_system(const Ctx& c, const Inst& I, double delta_w, double* tile, double* Qs) {
+  resolve_edges(c, I, tile);
+  riccati_vector(c, I, delta_w, Qs);
+  forward_recover(c, I, I.rest, delta_w, 0, 1, tile);
+}
+
+// filter acceptance test of a trial point (Waechter & Biegler 2006, Sec. 2.3): 0 = rejected, 1 = accepted (the filter gets
+// augmented), 2 = accepted under the Armijo condition
+DMB_DEV int trial_acceptable(const DmbOptions& o, const DmbShared* S, double theta_t, double phi_t, double theta, double phi,
+                             double dphi, double alpha, double theta_max, double theta_min) {
+  const double eps_r = 10.0 * 2.220446049250313e-16;
+  if (!(phi_t == phi_t && phi_t < INFINITY && theta_t <= theta_max)) return 0;
+  const bool switching = (dphi < 0.0) && (alpha * pow(-dphi, o.s_phi) > o.delta * pow(theta, o.s_theta));
+  bool ok; int kind;
+  if (theta <= theta_min && switching) { ok = (phi_t - phi - eps_r * fabs(phi) <= o.eta_phi * alpha * dphi); kind = 2; }
+  else {
+    ok = (theta_t - (1.0 - o.gamma_theta) * theta <= eps_r * fabs(theta)) || (phi_t - (phi - o.gamma_phi * theta) <= eps_r * fabs(phi));
+    kind = 1;
+  }
+  if (ok) for (int k = 0; k < S->n_filt; ++k) if (!(theta_t < S->filt_theta[k] || phi_t < S->filt_phi[k])) { ok = false; break; }
+  return ok ? kind : 0;
+}
+
+// largest step in [0,1] that keeps every bounded primal variable and slack a fraction tau inside its bounds
+DMB_DEV double primal_ftb(const Ctx& c, const Inst& I, const double* dw, const double* ds, double tau, double* red) {
+  double a = 1.0;
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const double d = dw[i];
+    if (I.lb[i] > -DMB_INF) a = fmin(a, ftb_step(I.w[i] - I.lb[i], d, tau));
+    if (I.ub[i] < DMB_INF) a = fmin(a, ftb_step(I.ub[i] - I.w[i], -d, tau));
+  }
+#if NNL > 0
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) a = fmin(a, ftb_step(nl_ub_relaxed(I, i / NNL, i % NNL) - I.s[i], -ds[i], tau));
+#else
+  (void)ds;
+#endif
+  return block_min(c, a, red);
+}
+
+// dual step size: fraction-to-the-boundary for the bound multipliers along dz = mu/s - z -+ z/s * d (d from dw / ds)
+DMB_DEV double dual_ftb(const Ctx& c, const Inst& I, const double* dw, const double* ds, double mu, double tau, double* red) {
+  double a_z = 1.0;
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const double d = dw[i];
+    if (I.lb[i] > -DMB_INF) { const double sl = I.w[i] - I.lb[i]; a_z = fmin(a_z, ftb_step(I.zL[i], mu / sl - I.zL[i] - I.zL[i] / sl * d, tau)); }
+    if (I.ub[i] < DMB_INF) { const double su = I.ub[i] - I.w[i]; a_z = fmin(a_z, ftb_step(I.zU[i], mu / su - I.zU[i] + I.zU[i] / su * d, tau)); }
+  }
+#if NNL > 0
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - I.s[i];
+    a_z = fmin(a_z, ftb_step(I.vU[i], mu / su - I.vU[i] + I.vU[i] / su * ds[i], tau));
+  }
+#else
+  (void)ds;
+#endif
+  return block_min(c, a_z, red);
+}
+
 // lam_g0 / lam_x0 (flat reference layouts, may be NULL): the multipliers of a previous solution; used only with
 // o.warm_start (IPOPT warm_start_init_point=yes: the point is pushed by warm_start_bound_push/frac, the multipliers are taken
 // over — bound multipliers at least warm_start_mult_bound_push —, no least-squares estimate, mu starts at mu_init).
+//
+// One loop, four modes, so that every phase of the KKT solve is instantiated ONCE in the kernel:
+//   MODE_SCALE  first pass: gradient-based scaling from the derivatives at the user's point, bound push, slack start
+//   MODE_LS     least-squares multiplier estimate (cold start, and after a restoration): H := I, g := grad f - zL + zU
+//   MODE_NORMAL an interior-point iteration (convergence test, mu update, step, refinement, filter line search with
+//               second-order correction)
+//   MODE_RESTO  an iteration of the feasibility restoration substitute (oracle/ipm.py::_restoration): same KKT solve with the
+//               barrier terms of the restoration problem (resto_terms); objective and multipliers off through df = 0, lam = 0
+enum { MODE_NORMAL = 0, MODE_LS = 1, MODE_RESTO = 2, MODE_SCALE = 3 };
 DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o, const double* x0_internal,
                             double* tile, double* Qs, DmbShared* S, DmbResult* out,
                             const double* lam_g0 = nullptr, const double* lam_x0 = nullptr) {
@@ -96,183 +180,256 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
 #else
   I.sub = nullptr;
 #endif
-  // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
   for (int i = c.tid; i < NWI; i += c.nthr) { I.w[i] = x0_internal[i]; I.zL[i] = 0.0; I.zU[i] = 0.0; }
   for (int i = c.tid; i < NLAM; i += c.nthr) { I.dc[i] = 1.0; I.lam[i] = 0.0; }
   I.df = 1.0;
-  CTA_SYNC();
-  eval_derivatives(c, I);
-  {
-    double g = 0.0;
-    for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.go[i]));
-    g = block_max(c, g, red);
-    if (g > o.nlp_scaling_max_gradient) I.df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
-  }
-  for (int e = c.tid; e < NEDGE; e += c.nthr) {
-    double q[NQ], jnz[DMB_NNZ_J > 0 ? DMB_NNZ_J : 1], mx[NY > 0 ? NY : 1];
-    gather_q(I.w, e, q);
-    gen_J(q, edge_tvp(I.p, e), edge_pp(I.p, e), jnz);
-    for (int i = 0; i < NY; ++i) mx[i] = 0.0;
-    for (int k = 0; k < DMB_NNZ_J; ++k) mx[DMB_J_ROW[k]] = fmax(mx[DMB_J_ROW[k]], fabs(jnz[k]));
-    for (int i = 0; i < NY; ++i)
-      I.dc[LAM_EDGE(e) + i] = mx[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / mx[i], o.nlp_scaling_min_value) : 1.0;
-#if NNL > 0
-    double dnz[DMB_NNZ_D > 0 ? DMB_NNZ_D : 1], md[NNL];
-    gen_nl_jac(q, edge_tvp(I.p, e), edge_pp(I.p, e), dnz);
-    for (int i = 0; i < NNL; ++i) md[i] = 0.0;
-    for (int k = 0; k < DMB_NNZ_D; ++k) md[DMB_D_ROW[k]] = fmax(md[DMB_D_ROW[k]], fabs(dnz[k]));
-    for (int i = 0; i < NNL; ++i)
-      I.dc[LAM_EDGE(e) + NY + NX + i] = md[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / md[i], o.nlp_scaling_min_value) : 1.0;
-#endif
-  }
-  CTA_SYNC();
-  // ---- starting point: push into the (relaxed) bounds, slacks, bound multipliers ----------------------------
-  const bool ws = o.warm_start != 0 && lam_g0 != nullptr && lam_x0 != nullptr;
-  const double bpush = ws ? o.ws_bound_push : o.bound_push, bfrac = ws ? o.ws_bound_frac : o.bound_frac;
-  for (int i = c.tid; i < NWI; i += c.nthr) {
-    const double lo = I.lb[i], hi = I.ub[i];
-    const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
-    double v = I.w[i];
-    if (hl && hu) {
-      const double pl = fmin(bpush * fmax(1.0, fabs(lo)), bfrac * (hi - lo));
-      const double pu = fmin(bpush * fmax(1.0, fabs(hi)), bfrac * (hi - lo));
-      v = fmin(fmax(v, lo + pl), hi - pu);
-    } else if (hl) v = fmax(v, lo + bpush * fmax(1.0, fabs(lo)));
-    else if (hu) v = fmin(v, hi - bpush * fmax(1.0, fabs(hi)));
-    I.w[i] = v;
-    double zl = o.bound_mult_init_val, zu = o.bound_mult_init_val;
-    if (ws) {
-      const int fl = DMB_W2FLAT[i];
-      const double lx = fl >= 0 ? I.df * lam_x0[fl] : 0.0;             // lam_x = zU - zL (unscaled objective)
-      zl = fmin(fmax(-lx, o.ws_mult_bound_push), o.ws_mult_init_max);
-      zu = fmin(fmax(lx, o.ws_mult_bound_push), o.ws_mult_init_max);
-    }
-    I.zL[i] = hl ? zl : 0.0;
-    I.zU[i] = hu ? zu : 0.0;
-  }
-  if (ws) {
-    for (int i = c.tid; i < NLAM; i += c.nthr) {
-      const int fl = DMB_LAM2FLAT[i];
-      const double y = fl >= 0 ? I.df * lam_g0[fl] / I.dc[i] : 0.0;
-      I.lam[i] = fmin(fmax(y, -o.ws_mult_init_max), o.ws_mult_init_max);
-    }
-    CTA_SYNC();
-#if DMB_DISCRETE
-    for (int idx = c.tid; idx < NEDGE * NX; idx += c.nthr) {           // auxiliary end-of-interval rows: lam_G = lam_C
-      const int e = idx / NX, i = idx - e * NX;
-      I.lam[LAM_EDGE(e) + DMB_NZ + i] = I.lam[LAM_EDGE(e) + NY + i];
-    }
-#endif
-  }
-  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
-    I.s[i] = 0.0;
-    I.vU[i] = ws ? fmin(fmax(I.lam[LAM_EDGE(i / (NNL > 0 ? NNL : 1)) + NY + NX + i % (NNL > 0 ? NNL : 1)], o.ws_mult_bound_push), o.ws_mult_init_max)
-                 : o.bound_mult_init_val;
-  }
-  CTA_SYNC();
-  double f, theta, inf_pr;
-  eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
-#if NNL > 0
-  // slack init: s = d(x) pushed below the (relaxed) upper bound; residual d - s follows
-  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
-    const int e = i / NNL, j = i % NNL;
-    const double d = I.res[LAM_EDGE(e) + NY + NX + j];      // s was 0
-    const double hi = nl_ub_relaxed(I, e, j);
-    I.s[i] = fmin(d, hi - bpush * fmax(1.0, fabs(hi)));
-  }
-  CTA_SYNC();
-  eval_point(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
-#endif
   if (c.tid == 0) { S->fail = 0; S->n_filt = 0; }
   CTA_SYNC();
-  if (!ws) {
-  // ---- least-squares multiplier estimate ----------------------------------------------------------------------------
-  for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = 0.0;
-  CTA_SYNC();
-  eval_derivatives(c, I);                       // lam = 0: objective gradient and Jacobian at the pushed point
-  factor_edges(c, I, I.rest, 0.0, 0.0, 1, tile, &S->fail);
-  riccati_backward(c, I, 0.0, 0.0, 0.0, 1, Qs, &S->flag);
-  forward_recover(c, I, I.rest, 0.0, 1, 0, tile);
-  {
-    double m = 0.0;
-    for (int i = c.tid; i < NLAM; i += c.nthr) m = fmax(m, fabs(I.lamn[i]));
-    m = block_max(c, m, red);
-    const bool ok = (m <= o.constr_mult_init_max) && !S->flag && !S->fail && (m == m);
-    for (int i = c.tid; i < NLAM; i += c.nthr) I.lam[i] = ok ? I.lamn[i] : 0.0;
-  }
-  CTA_SYNC();
-  }
-
-  DMB_TICK(8);
+  const bool ws = o.warm_start != 0 && lam_g0 != nullptr && lam_x0 != nullptr;
+  double f = 0.0, theta = 0.0, inf_pr = 0.0;
   double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
-  const double theta_max = o.theta_max_fact * fmax(1.0, theta), theta_min = o.theta_min_fact * fmax(1.0, theta);
+  double theta_max = 0.0, theta_min = 0.0;
   double delta_w_last = 0.0;
   int it = 0, status = DMB_MAXIMUM_ITERATIONS_EXCEEDED, acceptable_cnt = 0, n_resto = 0;
   const int degenerate_reg = o.mimic_dummy_reg && DMB_HAS_DUMMIES;
   bool acceptable_now = false;
   double dual0 = 0.0;
+  int mode = MODE_SCALE;
+  // restoration state
+  double theta_ref = 0.0, df_save = 1.0;
+  int resto_it = 0;
+  bool after_resto = false;
 
   while (true) {
-    // ---- convergence tests ----------------------------------------------------------------------------------------------
     eval_derivatives(c, I);
-    DMB_TICK(0);
-    double dual, cmpl, s_d, s_c;
-    kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
-    dual0 = dual;
-    const double E0 = fmax(fmax(dual / s_d, inf_pr), cmpl / s_c);
-#ifdef DMB_HOSTSIM
-    if (dmb_hostsim_verbose) printf("%4d f=% .10e inf_pr=%.2e inf_du=%.2e cmpl=%.2e lg(mu)=%5.1f E0=%.2e theta=%.3e nfilt=%d\n", it, f / I.df, inf_pr, dual, cmpl, log10(mu), E0, theta, S->n_filt);
+    if (mode == MODE_SCALE) {
+      // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
+      {
+        double g = 0.0;
+        for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.go[i]));
+        g = block_max(c, g, red);
+        if (g > o.nlp_scaling_max_gradient) I.df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
+      }
+      for (int e = c.tid; e < NEDGE; e += c.nthr) {
+        // Jacobian nonzeros of this edge as left by eval_derivatives (dc = 1 so far: unscaled)
+        const double* eb = I.eb + (size_t)e * EB_SZ;
+        double mx[NY > 0 ? NY : 1];
+        for (int i = 0; i < NY; ++i) mx[i] = 0.0;
+        for (int k = 0; k < DMB_NNZ_J; ++k) mx[DMB_J_ROW[k]] = fmax(mx[DMB_J_ROW[k]], fabs(eb[EB_JNZ + k]));
+        for (int i = 0; i < NY; ++i)
+          I.dc[LAM_EDGE(e) + i] = mx[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / mx[i], o.nlp_scaling_min_value) : 1.0;
+#if NNL > 0
+        double md[NNL];
+        for (int i = 0; i < NNL; ++i) md[i] = 0.0;
+        for (int k = 0; k < DMB_NNZ_D; ++k) md[DMB_D_ROW[k]] = fmax(md[DMB_D_ROW[k]], fabs(eb[EB_DNZ + k]));
+        for (int i = 0; i < NNL; ++i)
+          I.dc[LAM_EDGE(e) + NY + NX + i] = md[i] > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / md[i], o.nlp_scaling_min_value) : 1.0;
 #endif
-    {
-      // unscaled secondary tolerances
-      double pu = 0.0;
-      for (int i = c.tid; i < NLAM; i += c.nthr) pu = fmax(pu, fabs(I.res[i]) / I.dc[i]);
-      pu = block_max(c, pu, red);
-      const double du_u = dual / I.df, cm_u = cmpl / I.df;
-      if (!(E0 == E0)) { status = DMB_INVALID_NUMBER_DETECTED; break; }
-      if (E0 <= o.tol && du_u <= o.dual_inf_tol && pu <= o.constr_viol_tol && cm_u <= o.compl_inf_tol) { status = DMB_SOLVE_SUCCEEDED; break; }
-      acceptable_now = (E0 <= o.acceptable_tol && du_u <= o.acceptable_dual_inf_tol && pu <= o.acceptable_constr_viol_tol && cm_u <= o.acceptable_compl_inf_tol);
-      if (acceptable_now) {
-        if (++acceptable_cnt >= o.acceptable_iter) { status = DMB_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
-      } else acceptable_cnt = 0;
-      if (it >= o.max_iter) { status = DMB_MAXIMUM_ITERATIONS_EXCEEDED; break; }
-    }
-    // ---- barrier parameter (monotone, repeated decrease allowed) ----------------------------------------------------
-    while (true) {
-      double dm, cmm, sd2, sc2;
-      kkt_error(c, I, mu, o.s_max, red, &dm, &cmm, &sd2, &sc2);
-      const double Emu = fmax(fmax(dm / sd2, inf_pr), cmm / sc2);
-      if (Emu <= o.kappa_eps * mu && mu > o.mu_min) {
-        double nm = fmax(o.tol / 10.0, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
-        nm = fmax(nm, o.mu_min);
-        if (nm >= mu) break;
-        mu = nm; tau = fmax(o.tau_min, 1.0 - mu);
-        if (c.tid == 0) S->n_filt = 0;
+      }
+      CTA_SYNC();
+      // ---- starting point: push into the (relaxed) bounds, slacks, bound multipliers ----------------------------
+      const double bpush = ws ? o.ws_bound_push : o.bound_push, bfrac = ws ? o.ws_bound_frac : o.bound_frac;
+      for (int i = c.tid; i < NWI; i += c.nthr) {
+        const double lo = I.lb[i], hi = I.ub[i];
+        const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
+        double v = I.w[i];
+        if (hl && hu) {
+          const double pl = fmin(bpush * fmax(1.0, fabs(lo)), bfrac * (hi - lo));
+          const double pu = fmin(bpush * fmax(1.0, fabs(hi)), bfrac * (hi - lo));
+          v = fmin(fmax(v, lo + pl), hi - pu);
+        } else if (hl) v = fmax(v, lo + bpush * fmax(1.0, fabs(lo)));
+        else if (hu) v = fmin(v, hi - bpush * fmax(1.0, fabs(hi)));
+        I.w[i] = v;
+        double zl = o.bound_mult_init_val, zu = o.bound_mult_init_val;
+        if (ws) {
+          const int fl = DMB_W2FLAT[i];
+          const double lx = fl >= 0 ? I.df * lam_x0[fl] : 0.0;             // lam_x = zU - zL (unscaled objective)
+          zl = fmin(fmax(-lx, o.ws_mult_bound_push), o.ws_mult_init_max);
+          zu = fmin(fmax(lx, o.ws_mult_bound_push), o.ws_mult_init_max);
+        }
+        I.zL[i] = hl ? zl : 0.0;
+        I.zU[i] = hu ? zu : 0.0;
+      }
+      if (ws) {
+        for (int i = c.tid; i < NLAM; i += c.nthr) {
+          const int fl = DMB_LAM2FLAT[i];
+          const double y = fl >= 0 ? I.df * lam_g0[fl] / I.dc[i] : 0.0;
+          I.lam[i] = fmin(fmax(y, -o.ws_mult_init_max), o.ws_mult_init_max);
+        }
         CTA_SYNC();
-      } else break;
+#if DMB_DISCRETE
+        for (int idx = c.tid; idx < NEDGE * NX; idx += c.nthr) {           // auxiliary end-of-interval rows: lam_G = lam_C
+          const int e = idx / NX, i = idx - e * NX;
+          I.lam[LAM_EDGE(e) + DMB_NZ + i] = I.lam[LAM_EDGE(e) + NY + i];
+        }
+#endif
+      }
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+        I.s[i] = 0.0;
+        I.vU[i] = ws ? fmin(fmax(I.lam[LAM_EDGE(i / (NNL > 0 ? NNL : 1)) + NY + NX + i % (NNL > 0 ? NNL : 1)], o.ws_mult_bound_push), o.ws_mult_init_max)
+                     : o.bound_mult_init_val;
+      }
+      CTA_SYNC();
+      eval_point_cold(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
+#if NNL > 0
+      // slack init: s = d(x) pushed below the (relaxed) upper bound; residual d - s follows
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+        const int e = i / NNL, j = i % NNL;
+        const double d = I.res[LAM_EDGE(e) + NY + NX + j];      // s was 0
+        const double hi = nl_ub_relaxed(I, e, j);
+        I.s[i] = fmin(d, hi - bpush * fmax(1.0, fabs(hi)));
+      }
+      CTA_SYNC();
+      eval_point_cold(c, I, I.w, I.s, I.res, red, &f, &theta, &inf_pr);
+#endif
+      theta_max = o.theta_max_fact * fmax(1.0, theta); theta_min = o.theta_min_fact * fmax(1.0, theta);
+      mode = ws ? MODE_NORMAL : MODE_LS;
+      DMB_TICK(8);
+      continue;
+    }
+    DMB_TICK(0);
+    if (mode == MODE_NORMAL) {
+      // ---- convergence tests ----------------------------------------------------------------------------------------------
+      double dual, cmpl, s_d, s_c;
+      kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
+      dual0 = dual;
+      const double E0 = fmax(fmax(dual / s_d, inf_pr), cmpl / s_c);
+#ifdef DMB_HOSTSIM
+      if (dmb_hostsim_verbose) printf("%4d f=% .10e inf_pr=%.2e inf_du=%.2e cmpl=%.2e lg(mu)=%5.1f E0=%.2e theta=%.3e nfilt=%d\n", it, f / I.df, inf_pr, dual, cmpl, log10(mu), E0, theta, S->n_filt);
+#endif
+      {
+        // unscaled secondary tolerances
+        double pu = 0.0;
+        for (int i = c.tid; i < NLAM; i += c.nthr) pu = fmax(pu, fabs(I.res[i]) / I.dc[i]);
+        pu = block_max(c, pu, red);
+        const double du_u = dual / I.df, cm_u = cmpl / I.df;
+        if (!(E0 == E0)) { status = DMB_INVALID_NUMBER_DETECTED; break; }
+        if (E0 <= o.tol && du_u <= o.dual_inf_tol && pu <= o.constr_viol_tol && cm_u <= o.compl_inf_tol) { status = DMB_SOLVE_SUCCEEDED; break; }
+        acceptable_now = (E0 <= o.acceptable_tol && du_u <= o.acceptable_dual_inf_tol && pu <= o.acceptable_constr_viol_tol && cm_u <= o.acceptable_compl_inf_tol);
+        if (acceptable_now) {
+          if (++acceptable_cnt >= o.acceptable_iter) { status = DMB_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
+        } else acceptable_cnt = 0;
+        if (it >= o.max_iter) { status = DMB_MAXIMUM_ITERATIONS_EXCEEDED; break; }
+      }
+      // ---- barrier parameter (monotone, repeated decrease allowed) ----------------------------------------------------
+      while (true) {
+        double dm, cmm, sd2, sc2;
+        kkt_error(c, I, mu, o.s_max, red, &dm, &cmm, &sd2, &sc2);
+        const double Emu = fmax(fmax(dm / sd2, inf_pr), cmm / sc2);
+        if (Emu <= o.kappa_eps * mu && mu > o.mu_min) {
+          double nm = fmax(o.tol / 10.0, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+          nm = fmax(nm, o.mu_min);
+          if (nm >= mu) break;
+          mu = nm; tau = fmax(o.tau_min, 1.0 - mu);
+          if (c.tid == 0) S->n_filt = 0;
+          CTA_SYNC();
+        } else break;
+      }
     }
     DMB_TICK(1);
-    // ---- search direction ------------------------------------------------------------------------------------------------
+    // ---- search direction: one KKT solve in the mode's setting ---------------------------------------------------------------
+    const int lsm = mode == MODE_LS;
+    const double mu_k = lsm ? 0.0 : mu, kd_k = lsm ? 0.0 : o.kappa_d;
+    if (lsm) for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = 0.0;
     if (c.tid == 0) S->fail = 0;
     CTA_SYNC();
-    factor_edges(c, I, I.res, mu, o.kappa_d, 0, tile, &S->fail);
+    const double* rhs_c = lsm ? I.rest : I.res;
+    factor_edges(c, I, rhs_c, mu_k, kd_k, lsm, tile, &S->fail);
     DMB_TICK(2);
     double delta_w = 0.0;
-    if (degenerate_reg) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
+    if (mode == MODE_NORMAL && degenerate_reg) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
     bool step_fail = S->fail != 0;
     while (!step_fail) {
-      riccati_backward(c, I, mu, o.kappa_d, delta_w, 0, Qs, &S->flag);
+      riccati_backward(c, I, mu_k, kd_k, delta_w, lsm, Qs, &S->flag);
       const int wrong_inertia = S->flag;      // (re-set only behind the barrier at the top of the next call)
       if (!wrong_inertia) break;
+      if (mode != MODE_NORMAL) { step_fail = true; break; }      // LS / restoration: the Hessian is a positive diagonal
       if (delta_w == 0.0) delta_w = delta_w_last == 0.0 ? o.delta_w_first : fmax(o.delta_w_min, o.kappa_w_minus * delta_w_last);
       else delta_w *= (delta_w_last == 0.0 ? o.kappa_w_plus_first : o.kappa_w_plus);
       if (delta_w > o.delta_w_max) step_fail = true;
     }
-    // IPOPT: a failure at a point that satisfies the acceptable tolerances terminates as "acceptable"
-    if (step_fail) { status = acceptable_now ? DMB_SOLVED_TO_ACCEPTABLE_LEVEL : DMB_ERROR_IN_STEP_COMPUTATION; break; }
-    if (delta_w > 0.0) delta_w_last = delta_w;
+    if (mode == MODE_NORMAL) {
+      // IPOPT: a failure at a point that satisfies the acceptable tolerances terminates as "acceptable"
+      if (step_fail) { status = acceptable_now ? DMB_SOLVED_TO_ACCEPTABLE_LEVEL : DMB_ERROR_IN_STEP_COMPUTATION; break; }
+      if (delta_w > 0.0) delta_w_last = delta_w;
+    }
     DMB_TICK(3);
-    forward_recover(c, I, I.res, delta_w, 0, 0, tile);
+    if (!step_fail) forward_recover(c, I, rhs_c, delta_w, lsm, 0, tile);
+
+    if (mode == MODE_LS) {
+      // ---- least-squares multiplier estimate --------------------------------------------------------------------------------
+      double m = 0.0;
+      if (!step_fail) for (int i = c.tid; i < NLAM; i += c.nthr) m = fmax(m, fabs(I.lamn[i]));
+      m = block_max(c, m, red);
+      const bool ok = !step_fail && (m <= o.constr_mult_init_max) && (m == m);
+      for (int i = c.tid; i < NLAM; i += c.nthr) I.lam[i] = ok ? I.lamn[i] : 0.0;
+      CTA_SYNC();
+      mode = MODE_NORMAL;
+      if (after_resto) { after_resto = false; ++it; }
+      DMB_TICK(8);
+      continue;
+    }
+
+    if (mode == MODE_RESTO) {
+      // ---- one step of the feasibility restoration: fraction-to-the-boundary, Armijo backtracking on theta --------------------
+      bool leave = false, success = false;
+      if (step_fail) leave = true;
+      else {
+        double a = primal_ftb(c, I, I.dw, I.ds, tau, red);
+        double f_t = 0.0, theta_t = theta, infpr_t = inf_pr;
+        bool improved = false;
+        while (a > 1e-10) {
+          for (int i = c.tid; i < NWI; i += c.nthr) I.wt[i] = I.w[i] + a * I.dw[i];
+          for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.s[i] + a * I.ds[i];
+          CTA_SYNC();
+          eval_point_cold(c, I, I.wt, I.st, I.rest, red, &f_t, &theta_t, &infpr_t);
+          if (theta_t < (1.0 - 1e-4 * a) * theta) { improved = true; break; }
+          a *= 0.5;
+        }
+#ifdef DMB_HOSTSIM
+        if (dmb_hostsim_verbose) printf("     resto %d: theta %.6e -> %.6e alpha=%.3e improved=%d\n", resto_it, theta, theta_t, a, (int)improved);
+#endif
+        if (!improved) leave = true;
+        else {
+          for (int i = c.tid; i < NWI; i += c.nthr) I.w[i] = I.wt[i];
+          for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.s[i] = I.st[i];
+          for (int i = c.tid; i < NLAM; i += c.nthr) I.res[i] = I.rest[i];
+          theta = theta_t; inf_pr = infpr_t;
+          CTA_SYNC();
+          if (theta <= o.kappa_resto * theta_ref && theta <= theta_max) {
+            // acceptable to the (already augmented) filter of the outer problem?  needs the real objective
+            I.df = df_save;
+            eval_point_cold(c, I, I.w, I.s, I.rest, red, &f_t, &theta_t, &infpr_t);
+            I.df = 0.0;
+            const double phi_t = barrier_phi(c, I, I.w, I.s, mu, o.kappa_d, f_t, red);
+            bool okf = phi_t == phi_t && phi_t < INFINITY;
+            if (okf) for (int k = 0; k < S->n_filt; ++k) if (!(theta < S->filt_theta[k] || phi_t < S->filt_phi[k])) { okf = false; break; }
+            if (okf) { leave = true; success = true; f = f_t; }
+          }
+          if (!leave && ++resto_it >= o.resto_max_iter) leave = true;
+        }
+      }
+      if (!leave) continue;
+      // ---- leave the restoration; on failure the outer iterate comes back -----------------------------------------------------------
+      if (!success) {
+        for (int i = c.tid; i < NWI; i += c.nthr) I.w[i] = I.go[i];
+        for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.s[i] = I.s2[i];
+      }
+      CTA_SYNC();
+      I.df = df_save; I.resto = 0;
+      if (!success) {
+        status = theta_ref > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED;
+        theta = theta_ref;
+        break;
+      }
+      // bound multipliers capped, equality multipliers from a least-squares estimate at the restored point
+      for (int i = c.tid; i < NWI; i += c.nthr) { I.zL[i] = fmin(I.zL[i], 1e3); I.zU[i] = fmin(I.zU[i], 1e3); }
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.vU[i] = fmin(I.vU[i], 1e3);
+      CTA_SYNC();
+      mode = MODE_LS; after_resto = true;
+      continue;
+    }
+
     // ---- iterative refinement of the step (IPOPT: residual_ratio_max 1e-10) ------------------------------------------
     for (int ref_it = 0; ref_it < o.max_refine; ++ref_it) {
       double nr[3];
@@ -286,9 +443,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       for (int i = c.tid; i < NLAM; i += c.nthr) I.lamr[i] = I.lamn[i];
       for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.ds[i];
       CTA_SYNC();
-      resolve_edges(c, I, tile);
-      riccati_vector(c, I, delta_w, Qs);
-      forward_recover(c, I, I.rest, delta_w, 0, 1, tile);
+      resolve_system(c, I, delta_w, tile, Qs);
       for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];
       for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] += I.lamr[i];
       for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.ds[i] += I.st[i];
@@ -344,7 +499,6 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     double alpha = a_max, a_used = a_max;
     bool accepted = false, armijo = false;
     double f_t = f, theta_t = theta, infpr_t = inf_pr;
-    const double eps_r = 10.0 * 2.220446049250313e-16;
     int ls = 0;
     while (alpha >= a_min || ls == 0) {
       ++ls;
@@ -353,19 +507,57 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       CTA_SYNC();
       eval_point(c, I, I.wt, I.st, I.rest, red, &f_t, &theta_t, &infpr_t);
       const double phi_t = barrier_phi(c, I, I.wt, I.st, mu, o.kappa_d, f_t, red);
-      bool ok = false, arm = false;
-      if (phi_t == phi_t && phi_t < INFINITY && theta_t <= theta_max) {
-        const bool switching = (dphi < 0.0) && (alpha * pow(-dphi, o.s_phi) > o.delta * pow(theta, o.s_theta));
-        if (theta <= theta_min && switching) {
-          ok = (phi_t - phi - eps_r * fabs(phi) <= o.eta_phi * alpha * dphi); arm = true;
-        } else {
-          ok = (theta_t - (1.0 - o.gamma_theta) * theta <= eps_r * fabs(theta)) ||
-               (phi_t - (phi - o.gamma_phi * theta) <= eps_r * fabs(phi));
+      const int acc = trial_acceptable(o, S, theta_t, phi_t, theta, phi, dphi, alpha, theta_max, theta_min);
+      if (acc) { accepted = true; armijo = acc == 2; a_used = alpha; break; }
+      // ---- second-order correction on the first trial when the infeasibility did not decrease (W&B 2006, Sec. 2.4) -------------
+      if (ls == 1 && theta_t >= theta && o.max_soc > 0) {
+        // the corrected step solves the same system with c_soc in place of c: it is the primary step plus the solution for
+        // the right-hand side (0, c_soc - c).  Primary step kept in wt / lamr / st (the trial point is no longer needed).
+        for (int i = c.tid; i < NWI; i += c.nthr) { I.wt[i] = I.dw[i]; I.gl[i] = 0.0; }
+        for (int i = c.tid; i < NLAM; i += c.nthr) { I.lamr[i] = I.lamn[i]; I.rest[i] = (alpha - 1.0) * I.res[i] + I.rest[i]; }
+        for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.ds[i];
+        CTA_SYNC();
+        double theta_old = theta_t;
+        for (int soc_it = 0; soc_it < o.max_soc; ++soc_it) {
+          resolve_system(c, I, delta_w, tile, Qs);
+          for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];
+          for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] += I.lamr[i];
+          for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.ds[i] += I.st[i];
+          CTA_SYNC();
+          const double a_soc = primal_ftb(c, I, I.dw, I.ds, tau, red);
+          for (int i = c.tid; i < NWI; i += c.nthr) I.gl[i] = I.w[i] + a_soc * I.dw[i];
+          for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.s2[i] = I.s[i] + a_soc * I.ds[i];
+          CTA_SYNC();
+          double f2, th2, ip2;
+          eval_point_cold(c, I, I.gl, I.s2, I.soc, red, &f2, &th2, &ip2);
+          const double phi2 = barrier_phi(c, I, I.gl, I.s2, mu, o.kappa_d, f2, red);
+          const int acc2 = trial_acceptable(o, S, th2, phi2, theta, phi, dphi, alpha, theta_max, theta_min);
+#ifdef DMB_HOSTSIM
+          if (dmb_hostsim_verbose) printf("     soc %d: a_soc=%.3e theta %.6e -> %.6e acc=%d\n", soc_it, a_soc, theta_t, th2, acc2);
+#endif
+          if (acc2) {
+            accepted = true; armijo = acc2 == 2; a_used = a_soc;
+            for (int i = c.tid; i < NWI; i += c.nthr) I.wt[i] = I.gl[i];
+            for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.s2[i];
+            for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = I.soc[i];
+            f_t = f2; theta_t = th2; infpr_t = ip2;
+            CTA_SYNC();
+            a_z = dual_ftb(c, I, I.dw, I.ds, mu, tau, red);          // the whole direction is replaced, multipliers included
+            break;
+          }
+          if (th2 > o.kappa_soc * theta_old || soc_it + 1 == o.max_soc) break;
+          theta_old = th2;
+          // next correction: c_soc <- a_soc c_soc + c(x_soc);  right-hand side (0, c_soc - c)
+          for (int i = c.tid; i < NWI; i += c.nthr) I.gl[i] = 0.0;
+          for (int i = c.tid; i < NLAM; i += c.nthr) I.rest[i] = a_soc * (I.rest[i] + I.res[i]) + I.soc[i] - I.res[i];
+          CTA_SYNC();
         }
-        if (ok) for (int k = 0; k < S->n_filt; ++k) if (!(theta_t < S->filt_theta[k] || phi_t < S->filt_phi[k])) { ok = false; break; }
+        if (accepted) break;
+        for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] = I.wt[i];     // back to the primary step
+        for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] = I.lamr[i];
+        for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.ds[i] = I.st[i];
+        CTA_SYNC();
       }
-      if (ok) { accepted = true; armijo = arm; a_used = alpha; break; }
-      // TODO(second-order correction): the oracle applies it on the first trial when theta grows; see DESIGN.md
       alpha *= o.alpha_red_factor;
     }
     CTA_SYNC();                     // all threads are done reading the filter before thread 0 augments it
@@ -374,10 +566,24 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     if (dmb_hostsim_verbose) printf("     alpha=%.3e a_max=%.3e a_z=%.3e ls=%d dphi=%.3e phi=%.12e a_min=%.3e accepted=%d armijo=%d delta_w=%.1e\n", a_used, a_max, a_z, ls, dphi, phi, a_min, (int)accepted, (int)armijo, delta_w);
 #endif
     if (!accepted) {
-      // restoration substitute is not implemented on the device: report like the oracle does when it fails
+      // ---- enter the feasibility restoration (IPOPT: called at an acceptable point -> terminate as acceptable) -------------
       ++n_resto;
-      status = acceptable_now ? DMB_SOLVED_TO_ACCEPTABLE_LEVEL : (theta > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED);
-      break;
+      if (acceptable_now) { status = DMB_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
+      if (o.resto_max_iter <= 0) { status = theta > 1e-6 ? DMB_INFEASIBLE_PROBLEM_DETECTED : DMB_RESTORATION_FAILED; break; }
+      if (c.tid == 0) {
+        int k = S->n_filt < MAX_FILTER ? S->n_filt++ : MAX_FILTER - 1;
+        S->filt_theta[k] = (1.0 - o.gamma_theta) * theta; S->filt_phi[k] = phi - o.gamma_phi * theta;
+      }
+      // the restoration iterates in place (w, s); the point it starts from — the reference x_R of the proximal term, restored
+      // if the phase fails — is kept in the storage of `go` (no objective gradient is needed while df = 0) and `s2`
+      theta_ref = theta; resto_it = 0; df_save = I.df;
+      for (int i = c.tid; i < NWI; i += c.nthr) I.go[i] = I.w[i];
+      for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.s2[i] = I.s[i];
+      for (int i = c.tid; i < NLAM; i += c.nthr) I.lam[i] = 0.0;
+      CTA_SYNC();
+      I.df = 0.0; I.zeta = sqrt(mu); I.resto = 1;
+      mode = MODE_RESTO;
+      continue;
     }
     // ---- accept ------------------------------------------------------------------------------------------------------------------
     if (!armijo && c.tid == 0) {

@@ -47,6 +47,7 @@ DMS_DEV int dms_integrate(double* x, double* z, const double* u, const double* t
 #if DMS_DISCRETE
   double fa[SN > 0 ? SN : 1], jac[SN * SN > 0 ? SN * SN : 1];
 #if SNZ > 0
+  int converged = 0;
   for (int it = 0; it < newton_max; ++it) {            // algebraic equations 0 = g(x, u, z) for z
     gen_sim_fa(x, u, z, tvp, pp, fa);
     gen_sim_jac(x, u, z, tvp, pp, jac);
@@ -55,8 +56,10 @@ DMS_DEV int dms_integrate(double* x, double* z, const double* u, const double* t
     if (!dms_gauss(A, SNZ, SNZ + 1)) return 1;
     double nrm = 0.0;
     for (int i = 0; i < SNZ; ++i) { z[i] += A[i * (SNZ + 1) + SNZ]; nrm = fmax(nrm, fabs(A[i * (SNZ + 1) + SNZ]) / (1.0 + fabs(z[i]))); }
-    if (nrm < newton_tol) break;
+    if (!(nrm == nrm)) return 1;
+    if (nrm < newton_tol) { converged = 1; break; }
   }
+  if (!converged) return 1;                            // an unconverged z must not be accepted (as in the continuous branch)
 #endif
   gen_sim_fa(x, u, z, tvp, pp, fa);
   for (int i = 0; i < SNX; ++i) x[i] = fa[i];

@@ -125,11 +125,24 @@ class Simulator:
     def set_initial_guess(self): pass
 
     # ---- compute --------------------------------------------------------------------------------------------------------------
-    def _call(self, X, U, Z, TV, PP, mode):
+    def _pw(self, PP, W, B):
+        """parameter row of the C ABI: [p | w] (process noise is constant over the step like a parameter)."""
+        m = self.model
+        if m.n_p + m.n_w == 0:
+            return None
+        out = np.zeros((B, m.n_p + m.n_w))
+        if m.n_p:
+            out[:, :m.n_p] = np.asarray(PP, dtype=np.float64).reshape(-1, m.n_p)
+        if m.n_w and W is not None:
+            out[:, m.n_p:] = np.asarray(W, dtype=np.float64).reshape(-1, m.n_w)
+        return out
+
+    def _call(self, X, U, Z, TV, PP, mode, W=None):
         m, s = self.model, self.settings
         c = lambda a, n: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, n)) if n else None
         X = c(X, m.n_x); B = X.shape[0]
-        U, Z, TV, PP = c(U, m.n_u), c(Z, m.n_z), c(TV, m.n_tvp), c(PP, m.n_p)
+        U, Z, TV = c(U, m.n_u), c(Z, m.n_z), c(TV, m.n_tvp)
+        PP = self._pw(PP, W, B)
         xn = np.empty((B, m.n_x)); zn = np.empty((B, max(m.n_z, 1))); aux = np.empty((B, max(m.n_aux, 1))); st = np.empty(B, dtype=np.int32)
         p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         rc = self.lib.dms_step_host(self._h, B, p(X), p(U), p(Z), p(TV), p(PP), float(s.t_step), int(s.n_substeps),
@@ -138,17 +151,18 @@ class Simulator:
             raise RuntimeError(f"do_mpc_b200 simulator error {rc}: {self.lib.dms_last_error(self._h).decode()}")
         return xn, zn[:, :m.n_z], aux[:, :m.n_aux], st
 
-    def make_step_batch(self, X, U, Z=None, tvp=None, p=None):
-        """Advance B plants by one t_step: X [B,n_x], U [B,n_u] (physical units) -> (X_next, Z_next, status)."""
+    def make_step_batch(self, X, U, Z=None, tvp=None, p=None, W=None):
+        """Advance B plants by one t_step: X [B,n_x], U [B,n_u] (physical units), optional process noise W [B,n_w]
+        -> (X_next, Z_next, status)."""
         m = self.model
         B = np.asarray(X).reshape(-1, m.n_x).shape[0]
         Z = np.tile(self._z0.full().ravel(), (B, 1)) if (Z is None and m.n_z) else Z
         tv = np.tile(self.tvp_fun(self._t0).full().ravel(), (B, 1)) if (tvp is None and m.n_tvp) else tvp
         pp = np.tile(self.p_fun(self._t0).full().ravel(), (B, 1)) if (p is None and m.n_p) else p
-        xn, zn, _, st = self._call(X, U, Z, tv, pp, 0)
+        xn, zn, _, st = self._call(X, U, Z, tv, pp, 0, W)
         return xn, zn, st
 
-    def make_step_batch_device(self, X, U, Z=None, tvp=None, p=None, out=None, stream=None):
+    def make_step_batch_device(self, X, U, Z=None, tvp=None, p=None, out=None, stream=None, W=None):
         """Device-resident step: CUDA float64 torch tensors in, dict(x, z, status) of CUDA tensors out; queued on `stream`
         (default: torch's current stream), no host synchronisation."""
         import torch
@@ -161,6 +175,9 @@ class Simulator:
             p = torch.as_tensor(self.p_fun(self._t0).full().ravel(), dtype=torch.float64, device=dev).repeat(B, 1)
         if m.n_z and Z is None:
             Z = torch.as_tensor(self._z0.full().ravel(), dtype=torch.float64, device=dev).repeat(B, 1)
+        if m.n_w:                                      # C ABI parameter row = [p | w]
+            W = torch.zeros(B, m.n_w, dtype=torch.float64, device=dev) if W is None else W
+            p = torch.cat([p, W], dim=1).contiguous() if m.n_p else W.contiguous()
         if out is None:
             out = {"x": torch.empty(B, m.n_x, dtype=torch.float64, device=dev), "z": torch.empty(B, max(m.n_z, 1), dtype=torch.float64, device=dev),
                    "status": torch.empty(B, dtype=torch.int32, device=dev)}
@@ -191,7 +208,11 @@ class Simulator:
         assert u0.size == m.n_u, f"u0 has incorrect shape. You have: {u0.shape}, expected: {(m.n_u, 1)}"
         tvp0, p0, t0 = self.tvp_fun(self._t0), self.p_fun(self._t0), self._t0
         x0 = self._x0.full().ravel()
-        xn, zn, aux, st = self._call(x0, u0.ravel(), self._z0.full().ravel(), tvp0.full().ravel(), p0.full().ravel(), 0)
+        w = None
+        if w0 is not None:
+            w = np.asarray(w0.full() if hasattr(w0, "full") else w0, dtype=float).ravel()
+            assert w.size == m.n_w, f"w0 has incorrect shape. You have: {w.shape}, expected: {(m.n_w, 1)}"
+        xn, zn, aux, st = self._call(x0, u0.ravel(), self._z0.full().ravel(), tvp0.full().ravel(), p0.full().ravel(), 0, w)
         if st[0] != 0:
             raise RuntimeError("simulator.make_step: Newton iteration of the integrator failed")
         v = np.zeros(m.n_v) if v0 is None else np.asarray(v0, dtype=float).ravel()

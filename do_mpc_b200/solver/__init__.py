@@ -88,6 +88,7 @@ class BatchedNlpSolver:
         rc = self.lib.dmb_set_options(self._h, ctypes.byref(self.options), ctypes.sizeof(DmbOptions))
         self._check(rc)
         self._bounds_key = None
+        self.bounds_source = None        # callable -> (lbx, ubx); set by MPC.create_nlp so that the device entry points see `mpc.bounds[...] = v`
         self._stats = {"success": False, "return_status": "Not_Run", "iter_count": 0, "t_wall_total": 0.0}
         self.n_launches_timed = 0
 
@@ -118,6 +119,16 @@ class BatchedNlpSolver:
             assert lbx.size == self.n_w and ubx.size == self.n_w, "bounds must have n_w entries"
             self._check(self.lib.dmb_set_bounds(self._h, _ptr(lbx), _ptr(ubx)))
             self._bounds_key = key
+
+    def _refresh_bounds(self, lbx=None, ubx=None):
+        """Bounds for the device entry points: explicit arguments, else the owner's current bounds (`bounds_source`).
+        One launch per handle may be in flight at a time (workspace slots, work counter and staging are per handle)."""
+        if lbx is None and self.bounds_source is not None:
+            lbx, ubx = self.bounds_source()
+        if lbx is not None:
+            self._set_bounds(lbx, ubx)
+        elif self._bounds_key is None:
+            raise RuntimeError("do_mpc_b200: no bounds known to the solver — pass lbx/ubx or call _set_bounds first")
 
     # ---- batched host entry point --------------------------------------------------------------------------------
     def solve_batch(self, P, x0s=None, u0s=None, z0s=None, lbx=None, ubx=None, x_init=None, return_full=False, lam_g0=None, lam_x0=None):
@@ -151,10 +162,13 @@ class BatchedNlpSolver:
         return out
 
     # ---- device-resident entry point (torch tensors as memory containers) ----------------------------------------------
-    def solve_batch_device(self, P, x0s=None, u0s=None, z0s=None, x_init=None, out=None, stream=None, want_full=False, lam_g0=None, lam_x0=None):
+    def solve_batch_device(self, P, x0s=None, u0s=None, z0s=None, x_init=None, out=None, stream=None, want_full=False, lam_g0=None, lam_x0=None,
+                           lbx=None, ubx=None):
         """All arguments are CUDA float64 torch tensors on this solver's device; returns dict of CUDA tensors.
-        Asynchronous with respect to the host (kernel queued on `stream` or the current torch stream)."""
+        Asynchronous with respect to the host (kernel queued on `stream` or the current torch stream).  Bounds (host arrays,
+        shared by the batch): `lbx/ubx`, else the owning MPC's current bounds; uploaded only when they changed."""
         import torch
+        self._refresh_bounds(lbx, ubx)
         B = P.shape[0]
         dev = P.device
         def dp(t): return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -231,6 +245,7 @@ class BatchedNlpSolver:
     def sensitivities_device(self, x, lam_g, P, status=None, cols=None, u0_only=True, stream=None):
         """Device-resident variant (CUDA float64 torch tensors); returns dxdp as [B, ncols, n_u or n_w] (kernel layout)."""
         import torch
+        self._refresh_bounds()
         B, dev = P.shape[0], P.device
         def dp(t): return None if t is None else ctypes.c_void_p(t.data_ptr())
         cols_a = None if cols is None else np.ascontiguousarray(np.asarray(cols, dtype=np.int32).ravel())

@@ -50,7 +50,7 @@ def _sizes(r: Recipe, src: str, threads: int):
     ern = n_edge * (nx * nvp + nx + 2 * nvp * nvp + 2 * nvp) + n_node * (nv * nv + nv + nut * nxi + nut + nxi + 2 * nu + 4 * nu * nu)
     nwi = n_node * nvp + n_edge * ny
     nlam = nx + n_edge * (ny + nx + nnl)
-    vec = 7 * nwi + 6 * nlam + 4 * n_edge * nnl
+    vec = 7 * nwi + 7 * nlam + 5 * n_edge * nnl
     return tiles + qs + 128, ern, vec
 
 

@@ -19,7 +19,8 @@ Deliberate deviations from IPOPT (documented in DESIGN.md §Parity):
     slots, SURVEY.md App. B) are removed before the solve and keep their initial-guess value;
     IPOPT instead keeps them and regularises every iteration with delta_w = 1e-4/3^k — that
     schedule is reproduced here (`mimic_dummy_reg`) so iterates stay close;
-  * the restoration phase is replaced by a simpler feasibility-restoration (`_restoration`);
+  * the restoration phase is replaced by a simpler feasibility restoration (`_restoration`: primal barrier Newton steps
+    on the proximal feasibility problem; the CUDA kernel implements the same substitute);
   * no watchdog, no "tiny step" heuristics.
 """
 import time
@@ -28,6 +29,8 @@ from dataclasses import dataclass, field
 import numpy as np
 import scipy.sparse as sp
 from scipy.linalg import lapack
+
+from .blockldl import BlockLDL, BlockPartition
 
 
 @dataclass
@@ -86,6 +89,9 @@ class IpmOptions:
     kappa_resto: float = 0.9
     mimic_dummy_reg: bool = True
     verbose: bool = False
+    # KKT factorisation: "block" = block LDL^T on the scenario-tree partition (oracle/blockldl.py, exact inertia, sparse),
+    # "dense" = one LAPACK dsytrf of the whole matrix (the round-1 path; kept as the cross-check of the block path)
+    linear_solver: str = "block"
     # warm start (IPOPT warm_start_init_point = yes; defaults of the warm_start_* options)
     warm_start_init_point: bool = False
     warm_start_bound_push: float = 1e-3
@@ -167,6 +173,50 @@ class IPMSolver:
         self.id = np.where(~eq)[0]                  # inequality rows d_L <= d(x) <= d_U, slack s
         self.m_c, self.m_d = self.ic.size, self.id.size
         self.c_rhs = nlp.lbg[self.ic]
+        self.bp = self._partition() if o.linear_solver == "block" else None
+
+    def _partition(self):
+        """Block partition of the KKT unknowns [x | s | y_c | y_d] for oracle/blockldl.py: one block per scenario-tree
+        node (k, s) holding the node's own variables (_x[k,s,:], _u[k,s], _eps[k,s]) together with the collocation unknowns,
+        algebraic states, constraint rows and inequality slacks of the edge that ENDS in that node; leaves are eliminated
+        first, the root last.  With that grouping every diagonal block is a small KKT matrix with a square nonsingular
+        constraint Jacobian, so the block factorisation never meets a structurally singular pivot block.  Returns None for
+        NLP objects without the stage layout (then the dense factorisation is used)."""
+        nlp = self.nlp
+        if not all(hasattr(nlp, a) for a in ("ix_x", "ix_u", "ix_z", "edges", "n_scenarios")):
+            return None
+        N = nlp.N
+        off = np.concatenate([[0], np.cumsum(nlp.n_scenarios)]).astype(int)
+        n_nodes = int(off[-1])
+        nid = lambda k, s_: int(off[k] + min(s_, nlp.n_scenarios[k] - 1))
+        vb = np.zeros(nlp.n_w, dtype=np.int64)                     # node of every variable (dummies: irrelevant)
+        S = nlp.ix_x.shape[1]
+        for k in range(N + 1):
+            for s_ in range(S):
+                vb[nlp.ix_x[k, s_].ravel()] = nid(k, s_)
+        for k in range(N):
+            for s_ in range(S):
+                if nlp.ix_z.size: vb[nlp.ix_z[k, s_].ravel()] = nid(k + 1, s_)
+            for s_ in range(nlp.ix_u.shape[1]):
+                vb[nlp.ix_u[k, s_]] = nid(k, s_)
+        if nlp.ix_eps.size:
+            for k in range(nlp.ix_eps.shape[0]):
+                for s_ in range(S):
+                    vb[nlp.ix_eps[k, s_]] = nid(k, s_)
+        gb = np.zeros(nlp.n_g, dtype=np.int64)                     # node of every constraint row (init rows: root)
+        starts = [e[4] for e in nlp.edges] + [nlp.n_g]
+        for (k, s_, b, ch, row), nxt in zip(nlp.edges, starts[1:]):
+            gb[row:nxt] = nid(k + 1, ch)
+        node_of = np.concatenate([vb[self.iv], gb[self.id], gb[self.ic], gb[self.id]])
+        return BlockPartition(n_nodes - 1 - node_of)               # deepest nodes first, root last
+
+    def _factor(self, K):
+        """KKT factorisation with exact inertia: block LDL^T on the tree partition, dense dsytrf as fallback / cross-check."""
+        if self.bp is not None and self.bp.part.size == K.shape[0]:
+            kk = BlockLDL(K, self.bp)
+            if kk.ok or K.shape[0] > 3000:
+                return kk
+        return _KKT(K)
 
     # ---- problem functions on the reduced variable set, scaled ---------------------------------
     def _full(self, x):
@@ -256,7 +306,7 @@ class IPMSolver:
             rx = grad.copy(); rx[iL] -= zL; rx[iU] += zU
             rs = np.zeros(m_d); rs[jL] -= vL; rs[jU] += vU
             K = self._assemble(sp.csr_matrix((n, n)), np.ones(n), np.ones(m_d), Jc, Jd, 0.0)
-            kk = _KKT(K)
+            kk = self._factor(K)
             if kk.ok and kk.inertia[2] == 0:
                 sol = kk.solve(np.concatenate([rx, rs, np.zeros(m_c + m_d)]))
                 yc, yd = -sol[n + m_d:n + m_d + m_c], -sol[n + m_d + m_c:]
@@ -320,8 +370,9 @@ class IPMSolver:
                 print(f"{it:4d} f={f/self.df: .8e} inf_pr={prim:.2e} inf_du={dual:.2e} lg(mu)={np.log10(mu):5.1f} E0={E0:.2e}")
             if E0 <= o.tol and dual_u <= o.dual_inf_tol and prim_u <= o.constr_viol_tol and cmp_u <= o.compl_inf_tol:
                 status = "Solve_Succeeded"; break
-            if (E0 <= o.acceptable_tol and dual_u <= o.acceptable_dual_inf_tol
-                    and prim_u <= o.acceptable_constr_viol_tol and cmp_u <= o.acceptable_compl_inf_tol):
+            acceptable_now = (E0 <= o.acceptable_tol and dual_u <= o.acceptable_dual_inf_tol
+                              and prim_u <= o.acceptable_constr_viol_tol and cmp_u <= o.acceptable_compl_inf_tol)
+            if acceptable_now:
                 acceptable_cnt += 1
                 if acceptable_cnt >= o.acceptable_iter:
                     status = "Solved_To_Acceptable_Level"; break
@@ -363,7 +414,7 @@ class IPMSolver:
             fail = False
             while True:
                 K = self._assemble(W, Sx + delta_w, Ss + delta_w, Jc, Jd, delta_c)
-                kk = _KKT(K)
+                kk = self._factor(K)
                 npos, nneg, nzero = kk.inertia
                 if kk.ok and nzero == 0 and nneg == m_c + m_d:
                     break
@@ -376,7 +427,7 @@ class IPMSolver:
                 if delta_w > o.delta_w_max:
                     fail = True; break
             if fail:
-                status = "Error_In_Step_Computation"; break
+                status = "Solved_To_Acceptable_Level" if acceptable_now else "Error_In_Step_Computation"; break
             if delta_w > 0:
                 delta_w_last = delta_w
             sol = kk.solve(rhs)
@@ -468,6 +519,13 @@ class IPMSolver:
                             xt, st, ct, dt, ft = xt2, st2, ct2, dt2, ft2
                             sol = sol2
                             dyc, dyd = sol2[n + m_d:n + m_d + m_c], sol2[n + m_d + m_c:]
+                            # IPOPT replaces the whole search direction by the corrected one: the bound-multiplier
+                            # steps and their fraction-to-the-boundary step size follow the corrected primal step
+                            dzL = mu / sxl - zL - zL / sxl * dx2[iL]
+                            dzU = mu / sxu - zU + zU / sxu * dx2[iU]
+                            dvL = mu / ssl - vL - vL / ssl * ds2[jL]
+                            dvU = mu / ssu - vU + vU / ssu * ds2[jU]
+                            a_z = min(ftb(zL, dzL, tau), ftb(zU, dzU, tau), ftb(vL, dvL, tau), ftb(vU, dvU, tau))
                             break
                         if th2 > o.kappa_soc * th_old:
                             break
@@ -479,22 +537,22 @@ class IPMSolver:
             if not accepted:
                 # ---- restoration substitute ----
                 resto_count += 1
-                r = self._restoration(x, s, theta, filt, theta_max, mu)
+                if acceptable_now:               # IPOPT: "restoration phase called at acceptable point" -> acceptable termination
+                    status = "Solved_To_Acceptable_Level"; break
+                filt.append(((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta))    # IPOPT augments the filter first
+                r = self._restoration(x, s, theta, filt, theta_max, mu, barrier_phi)
                 if r is None:
-                    status = "Restoration_Failed" if theta > o.constr_viol_tol else "Infeasible_Problem_Detected"
-                    if theta > 1e-6:
-                        status = "Infeasible_Problem_Detected"
+                    status = "Infeasible_Problem_Detected" if theta > 1e-6 else "Restoration_Failed"
                     break
-                filt.append(((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta))
                 x, s = r
                 c, d = self._eval_g(x); f = self._eval_f(x); grad = self._eval_grad(x); Jc, Jd = self._eval_jac(x)
-                # multipliers: reset bound multipliers, least-squares y
-                zL[:] = np.minimum(zL, 1e3); zU[:] = np.minimum(zU, 1e3); vL[:] = np.minimum(vL, 1e3); vU[:] = np.minimum(vU, 1e3)
+                # multipliers: bound multipliers capped, least-squares y (as at the starting point)
+                zL = np.minimum(zL, 1e3); zU = np.minimum(zU, 1e3); vL = np.minimum(vL, 1e3); vU = np.minimum(vU, 1e3)
                 rx = grad.copy(); rx[iL] -= zL; rx[iU] += zU
                 rs = np.zeros(m_d); rs[jL] -= vL; rs[jU] += vU
                 Kls = self._assemble(sp.csr_matrix((n, n)), np.ones(n), np.ones(m_d), Jc, Jd, 0.0)
-                kls = _KKT(Kls)
-                yc[:] = 0; yd[:] = 0
+                kls = self._factor(Kls)
+                yc = np.zeros(m_c); yd = np.zeros(m_d)
                 if kls.ok and kls.inertia[2] == 0:
                     sol = kls.solve(np.concatenate([rx, rs, np.zeros(m_c + m_d)]))
                     yc_, yd_ = -sol[n + m_d:n + m_d + m_c], -sol[n + m_d + m_c:]
@@ -549,39 +607,48 @@ class IPMSolver:
             return (W + sp.diags(Dx)).tocsc()
         return sp.bmat(blocks, format="csc")
 
-    def _restoration(self, x, s, theta_ref, filt, theta_max, mu):
-        """Feasibility restoration substitute: damped Gauss-Newton on ||(c, d-s)||_2^2 with a proximal
-        term, inside the (relaxed) bounds by fraction-to-the-boundary, until theta <= kappa_resto*theta_ref
-        and the point is acceptable to the filter of the outer problem."""
+    def _restoration(self, x, s, theta_ref, filt, theta_max, mu, barrier_phi):
+        """Feasibility restoration substitute (IPOPT's own restoration phase — a nested interior-point solve of
+        min rho*||c||_1 + zeta/2*||D_R (x - x_R)||^2 — is third-party code that is not restated).  Primal barrier Newton
+        iteration on
+            min  zeta/2 ||D_R (x - x_R)||^2 + zeta/2 ||D_Rs (s - s_R)||^2 - mu sum log(bound slacks)   s.t.  c(x) = 0, d(x) - s = 0
+        with IPOPT's zeta = sqrt(mu), D_R = diag(1 / max(1, |x_R|)): every step satisfies the linearised constraints, so it is
+        a descent direction for theta = ||(c, d - s)||_1; fraction-to-the-boundary (outer tau) and Armijo backtracking on
+        theta.  Returns when theta <= kappa_resto * theta_ref and the point is acceptable to the (already augmented) filter
+        of the outer problem; None if theta cannot be reduced (local infeasibility) or after resto_max_iter steps.
+        The Hessian of this problem is a positive diagonal, so the KKT matrix always has the correct inertia."""
         o = self.o
         n, m_c, m_d = self.n, self.m_c, self.m_d
         iL, iU, xL, xU, jL, jU, dL, dU = self.iL, self.iU, self.xL, self.xU, self.jL, self.jU, self.dL, self.dU
         xr, sr = x.copy(), s.copy()
-        DR = 1.0 / np.maximum(1.0, np.abs(x))
         zeta = np.sqrt(mu)
+        DRx = zeta / np.maximum(1.0, np.abs(x)) ** 2
+        DRs = zeta / np.maximum(1.0, np.abs(s)) ** 2
+        tau = max(o.tau_min, 1.0 - mu)
         c, d = self._eval_g(xr)
         th = np.abs(c).sum() + np.abs(d - sr).sum()
+        W0 = sp.csr_matrix((n, n))
+
+        def ftb(v, dv):
+            neg = dv < 0
+            if not neg.any(): return 1.0
+            return min(1.0, float((-tau * v[neg] / dv[neg]).min()))
         for _ in range(o.resto_max_iter):
             Jc, Jd = self._eval_jac(xr)
-            # min 0.5||c + Jc dx||^2 + 0.5||d - s + Jd dx - ds||^2 + 0.5*zeta*||DR dx||^2 (+ tiny on ds)
-            A = sp.bmat([[Jc, None if m_d == 0 else sp.csr_matrix((m_c, m_d))],
-                         [Jd, -sp.identity(m_d)]] if m_d else [[Jc]], format="csr")
-            r = np.concatenate([c, d - sr])
-            reg = np.concatenate([zeta * DR ** 2 + 1e-10, np.full(m_d, 1e-8)])
-            # barrier-like damping towards the interior keeps steps inside the bounds
-            H = (A.T @ A + sp.diags(reg)).toarray()
-            gvec = A.T @ r
-            try:
-                step = -np.linalg.solve(H, gvec)
-            except np.linalg.LinAlgError:
+            sxl, sxu, ssl, ssu = xr[iL] - xL[iL], xU[iU] - xr[iU], sr[jL] - dL[jL], dU[jU] - sr[jU]
+            Sx = DRx.copy(); Sx[iL] += mu / sxl ** 2; Sx[iU] += mu / sxu ** 2
+            Ss = DRs.copy(); Ss[jL] += mu / ssl ** 2; Ss[jU] += mu / ssu ** 2
+            gx = DRx * (xr - x); gx[iL] -= mu / sxl; gx[iU] += mu / sxu
+            gs = DRs * (sr - s); gs[jL] -= mu / ssl; gs[jU] += mu / ssu
+            K = self._assemble(W0, Sx, Ss, Jc, Jd, 0.0)
+            kk = self._factor(K)
+            if not (kk.ok and kk.inertia[2] == 0):
                 return None
-            dx, ds = step[:n], step[n:]
-            def ftb(v, dv):
-                neg = dv < 0
-                if not neg.any(): return 1.0
-                return min(1.0, float((-0.99 * v[neg] / dv[neg]).min()))
-            a = min(ftb(xr[iL] - xL[iL], dx[iL]), ftb(xU[iU] - xr[iU], -dx[iU]),
-                    ftb(sr[jL] - dL[jL], ds[jL]) if m_d else 1.0, ftb(dU[jU] - sr[jU], -ds[jU]) if m_d else 1.0)
+            sol = kk.solve(-np.concatenate([gx, gs, c, d - sr]))
+            dx, ds = sol[:n], sol[n:n + m_d]
+            if not np.all(np.isfinite(sol)):
+                return None
+            a = min(ftb(sxl, dx[iL]), ftb(sxu, -dx[iU]), ftb(ssl, ds[jL]), ftb(ssu, -ds[jU]))
             improved = False
             while a > 1e-10:
                 xt, st = xr + a * dx, sr + a * ds
@@ -595,11 +662,8 @@ class IPMSolver:
                 return None
             xr, sr, c, d, th = xt, st, ct, dt, tht
             if th <= o.kappa_resto * theta_ref and th <= theta_max:
-                ft = self._eval_f(xr)
-                # filter check with the barrier objective of the outer problem
-                sl = (xr[iL] - xL[iL], xU[iU] - xr[iU], sr[jL] - dL[jL], dU[jU] - sr[jU])
-                ph = ft - mu * sum(np.log(v).sum() for v in sl)
-                if all((th < a_ or ph < b_) for a_, b_ in filt):
+                ph = barrier_phi(xr, sr, mu, self._eval_f(xr))
+                if np.isfinite(ph) and all((th < a_ or ph < b_) for a_, b_ in filt):
                     return xr, sr
         return None
 

@@ -1,0 +1,34 @@
+"""BASELINE.json configurations 1, 3, 4, 5 at their stated sizes on the GPU through the C ABI, against the oracle fixtures
+(tests/golden/cfg<k>_oracle.npz: 64 instances of each config's SURVEY §8d input distribution solved by oracle/ipm.py with
+second-order correction and restoration ON).  Required: equal success flags, |u0 - u0_oracle| <= 1e-5 * u_scaling and
+iteration counts within 1 on instances where both converge; basin mismatches of the non-convex swing-up problem are counted
+separately and bounded."""
+import numpy as np
+import pytest
+
+from config_cases import MAX_ITER, compare_with_oracle, config_mpc, fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", [1, 3, 4, 5])
+def test_config_matches_oracle_on_gpu(cfg):
+    mpc = config_mpc(cfg, setup=True)
+    fx = fixture(cfg)
+    n = fx["x0"].shape[0]
+    assert n >= 64
+    idx = np.arange(n)
+    mpc.S.set_options(max_iter=MAX_ITER)
+    out = mpc.make_step_batch(fx["x0"], fx["u_prev"], fx["z0"] if "z0" in fx else None, tvp=fx.get("tvp"))
+    r = mpc.recipe
+    res = compare_with_oracle(cfg, fx, idx, out["status"], out["iter_count"], out["u0"], r.u_scaling)
+    print(f"cfg{cfg}: {res['n_ok']}/{res['n']} converged in both, basin mismatches {res['basin']}, max iteration difference {res['iter_diff_max']}")
+    if cfg == 4:
+        # long non-convex solves are chaotic w.r.t. rounding (FMA contraction): a few instances may end in another basin
+        assert res["basin"] <= 0.1 * res["n_ok"], res
+        assert (res["iter_diff"][res["same_basin"]] <= 1).mean() >= 0.9, res
+    else:
+        assert res["basin"] == 0, res
+        assert res["iter_diff_max"] <= 1, res
+    info = mpc.S.launch_info()
+    assert info["n_launches"] >= 1 and info["grid"] >= 1

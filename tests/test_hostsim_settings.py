@@ -35,7 +35,7 @@ def _build(name):
     for k, v in kw.items():
         setattr(mpc.settings, k, v)
     if name == "terminal_bounds":
-        mpc.terminal_bounds["upper", "_x", "C_b"] = 1.2
+        mpc.terminal_bounds["upper", "C_b"] = 1.2          # reference form (_mpc.py:424-431)
     if name == "hard_nl_cons_colloc":
         mpc.set_nl_cons("T_K_hard", mpc.model.x["T_K"] - 0.5 * mpc.model.x["T_R"], ub=70.0)
     if name == "soft_nl_cons":
