@@ -5,18 +5,26 @@
 
 A "step" is one pass of the hot path over one batch: B cold-start NLP solves (nominal CSTR, N_horizon=20,
 collocation degree 2; x0/u_prev as SURVEY.md §8d: the 1000 shipped sampling-plan entries first, then
-U([0.1,0.1,50,50],[2,2,140,140]) x U([5,-8500],[100,0]) with np.random.seed(42)).  Weak scaling: every rank owns
-`--batch` instances; N>1 is launched by torchrun, one rank per GPU, and ends each step with one NCCL all-gather
-of the converged controls and status flags.
+U([0.1,0.1,50,50],[2,2,140,140]) x U([5,-8500],[100,0]) with np.random.seed(42)).  N>1 is launched by torchrun, one rank
+per GPU, and every step ends with one NCCL all-gather of the converged controls and status flags.
 
-`value`   : device-resident throughput (inputs already in HBM, CUDA events around the solve kernel, max over ranks).
+`value`   : device-resident throughput (inputs already in HBM, CUDA events around the step, max over ranks), WEAK scaling:
+            every rank owns `--batch` instances.
+`strong`  : the same measurement with the QUOTED batch (4096 instances in total) split over the N ranks (N > 1 only).
 `e2e`     : same metric through the public API MPC.make_step_batch with HOST buffers (H2D + solve + D2H per step).
-`--impl reference`: the CPU restatement of the reference path (oracle/, numpy; CasADi/IPOPT is not installable here)
-            on all host cores, bounded sample per step.
+`other_configs` : BASELINE configs 3, 4, 5 at their stated sizes, 2 timed steps each (N = 1 only).
+`roofline.traffic` : dram__bytes_read.sum + dram__bytes_write.sum of one solve-kernel launch, measured in this run by a
+            child process under `ncu` (N = 1; falls back to the committed capture when ncu cannot run).
+`--impl reference`: the CPU restatement of the reference path (oracle/, numpy + LAPACK; CasADi/IPOPT is not installable
+            here) on all host cores, one BLAS thread per process.
 """
+import os
+
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"          # BEFORE numpy is imported: the CPU arm runs one process per core, one BLAS thread each
+
 import argparse
 import json
-import os
 import subprocess
 import sys
 import threading
@@ -32,6 +40,7 @@ sys.path.insert(0, str(ROOT / "examples"))
 METRIC = "mpc_make_step_solves_per_sec"
 UNIT = "solves/s"
 WORKLOAD = "cstr_nominal_N20_deg2_batch{B}_cold_start"
+IPOPT_NOTE = "published IPOPT figure for this NLP: 45.6 ms/solve = 22 solves/s/core on unknown hardware (BASELINE.md)"
 
 
 def make_inputs(B, rank=0):
@@ -45,46 +54,58 @@ def make_inputs(B, rank=0):
     return x0, up
 
 
-# ---- CPU baseline: the oracle port on all host cores ------------------------------------------------------------
+# ---- CPU arm: the oracle port on all host cores ---------------------------------------------------------------------
 _W = {}
 
 
 def _cpu_worker(args):
     x0, up = args
     if "sol" not in _W:
-        os.environ.setdefault("OMP_NUM_THREADS", "1")
         from oracle import models
         from oracle.ipm import IPMSolver, IpmOptions
         from oracle.nlp import FlatNLP
         _W["nlp"] = FlatNLP(models.cstr_nominal())
         _W["sol"] = IPMSolver(_W["nlp"], IpmOptions(max_iter=300))
     from oracle.ipm import solve_mpc
+    t = time.perf_counter()
     r = solve_mpc(_W["nlp"], x0, up, solver=_W["sol"])
-    return r["success"], r["iter_count"]
+    return r["success"], r["iter_count"], time.perf_counter() - t
 
 
 class CpuPool:
-    """All host cores, one oracle solver per worker process (the reference's own idiom for parallel sampling:
-    examples/tools/sampling/multiprocessing/closed_loop/mp_sampling_closed_loop_02.py:21-24,69-70)."""
+    """All host cores, one oracle solver per worker process, one BLAS thread each (the reference's own idiom for parallel
+    sampling: examples/tools/sampling/multiprocessing/closed_loop/mp_sampling_closed_loop_02.py:21-24,69-70)."""
 
     def __init__(self, x0, up):
         import multiprocessing as mp
-        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-            os.environ[v] = "1"
         self.cores = os.cpu_count() or 1
         self.x0, self.up = x0, up
         self.pool = mp.get_context("fork").Pool(self.cores)
-        self.pool.map(_cpu_worker, [(x0[i], up[i]) for i in range(self.cores)])     # build the NLP per worker, untimed
+        # build the NLP per worker (untimed), then calibrate the rate on two instances per core
+        self.pool.map(_cpu_worker, [(x0[i % len(x0)], up[i % len(x0)]) for i in range(self.cores)], chunksize=1)
+        self.rate, _, _, _ = self.run(2 * self.cores)
+
+    def sample_size(self, B, seconds):
+        """the whole batch when it fits into `seconds` of wall time, else a bounded sample (multiple of the core count)"""
+        n = int(self.rate * seconds)
+        return B if n >= B else max(self.cores, (n // self.cores) * self.cores)
 
     def run(self, n_sample):
         n = len(self.x0)
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker, [(self.x0[i % n], self.up[i % n]) for i in range(n_sample)], chunksize=1)
         dt = time.perf_counter() - t0
-        return n_sample / dt, dt, float(np.mean([r[0] for r in res]))
+        return n_sample / dt, dt, float(np.mean([r[0] for r in res])), float(np.mean([r[2] for r in res]))
 
     def close(self):
         self.pool.close()
+
+
+def cpu_baseline_record(cp, v, dt, succ, t_solve, n_sample, B):
+    return {"value": v, "unit": UNIT, "cores": cp.cores, "kind": "port", "per_core": v / cp.cores,
+            "ms_per_solve_one_core": 1e3 * t_solve, "same_config": bool(n_sample == B),
+            "sample": f"{n_sample} of the {B} instances of the same batch per step ({dt:.1f} s), oracle/ipm.py (numpy restatement of IPOPT, "
+                      f"block LDL^T with exact inertia) on {cp.cores} processes x 1 BLAS thread; success rate {succ:.3f}; {IPOPT_NOTE}"}
 
 
 def clocks_sampler(stop, out):
@@ -95,17 +116,17 @@ def clocks_sampler(stop, out):
         try:
             r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", idx],
                                capture_output=True, text=True, timeout=5)
-            out.append([v.strip() for v in r.stdout.strip().split(",")])
+            out.append((time.perf_counter(), [v.strip() for v in r.stdout.strip().split(",")]))
         except Exception:
             pass
         stop.wait(0.1)
 
 
-def summarize_clocks(samples):
+def summarize_clocks(samples, t0=None, t1=None):
     sm, mx, reasons = [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for s in samples:
-        if len(s) < 7:
+    for t, s in samples:
+        if len(s) < 7 or (t0 is not None and not (t0 <= t <= t1)):
             continue
         try:
             sm.append(float(s[0])); mx.append(float(s[1]))
@@ -126,24 +147,111 @@ def run_reference(args):
     B = args.batch
     x0, up = make_inputs(B, 0)
     cp = CpuPool(x0, up)
-    n_sample = max(cp.cores, min(4 * cp.cores, 512))
+    n_sample = cp.sample_size(B, 25.0)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, succ = cp.run(n_sample)
+        v, dt, succ, ts = cp.run(n_sample)
         if i >= args.warmup:
-            vals.append((v, dt))
+            vals.append((v, dt, succ, ts))
     cp.close()
-    value = float(np.mean([v for v, _ in vals]))
+    value = float(np.mean([v[0] for v in vals])); dt = float(np.mean([v[1] for v in vals]))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.mean([dt for _, dt in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD.format(B=B), "parallelism": f"{cp.cores} host processes"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cp.cores, "kind": "port",
-                             "sample": f"{n_sample} instances per step of the same workload, oracle/ipm.py (numpy restatement of "
-                                       f"IPOPT; CasADi/IPOPT not installable offline; the reference's shipped dataset reports 45.6 ms per "
-                                       f"IPOPT solve = 22 solves/s/core on unknown hardware)"},
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD.format(B=B), "batch_per_step": n_sample, "global_batch": B, "n_horizon": 20,
+                       "collocation": "radau deg 2, ni 1", "n_w": 376, "n_g": 324, "start": "cold (set_initial_guess broadcast)",
+                       "parallelism": f"{cp.cores} host processes x 1 BLAS thread"},
+            "cpu_baseline": cpu_baseline_record(cp, value, dt, vals[-1][2], float(np.mean([v[3] for v in vals])), n_sample, B),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ---- BASELINE configs 3, 4, 5 at their stated sizes (same inputs as tools/run_configs.py) ------------------------------
+def other_config_cases():
+    import batch_reactor, dip, industrial_poly
+    rng = np.random.RandomState(0)
+    x3 = np.array([1.0, 0.5, 0.0, 120.0]) * rng.uniform(0.9, 1.1, size=(1024, 4))
+    x4 = np.zeros((8192, 6)); x4[:, 1:3] = 0.9 * np.pi * rng.uniform(0.9, 1.1, size=(8192, 2))
+    g = np.load(ROOT / "tests" / "golden" / "kkt_industrial_poly.npz")
+    x5 = g["x"][0] * rng.uniform(0.98, 1.02, size=(2048, 10))
+    return [("cfg3_batch_reactor_robust_N30_B1024", lambda: batch_reactor.reactor_mpc(n_horizon=30, n_robust=1), x3, np.zeros((1024, 1)), None, None),
+            ("cfg4_dip_N50_B8192", lambda: dip.dip_mpc(n_horizon=50), x4, np.zeros((8192, 1)), np.zeros((8192, 3)), np.full((51, 1), -0.8)),
+            ("cfg5_industrial_poly_robust_N20_B2048", lambda: industrial_poly.poly_mpc(), x5, np.zeros((2048, 3)), None, None)]
+
+
+def run_other_configs(dev, peak, flush, samples, steps=2):
+    import torch
+    out = {}
+    for name, make, X0, Up, Z0, tvp in other_config_cases():
+        mpc = make()
+        r, S = mpc.recipe, mpc.S
+        S.set_options(max_iter=300)
+        P, x0s, u0s, z0s = mpc.pack_batch(X0, Up, Z0, tvp=tvp)
+        dP, dx, du = (torch.tensor(a, device=dev) for a in (P, x0s, u0s))
+        dz = None if z0s is None else torch.tensor(z0s, device=dev)
+        B = X0.shape[0]
+        res = S.solve_batch_device(dP, dx, du, dz)                       # warm-up (also loads the library)
+        torch.cuda.synchronize()
+        ms = []
+        t_a = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); res = S.solve_batch_device(dP, dx, du, dz, out=res); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t_b = time.perf_counter()
+        it = res["iter_count"].cpu().numpy(); st = res["status"].cpu().numpy()
+        ok = (st == 0) | (st == 1)
+        A_B = 16 * (3 * r.n_w + r.n_g) + 8 * r.n_p
+        t = float(np.mean(ms)) * 1e-3
+        ach = A_B * float(it.sum() + B) / t / 1e9
+        out[name] = {"solves_per_s": B / t, "ms_per_step": t * 1e3, "batch": B, "n_w": r.n_w, "n_g": r.n_g, "edges": int(len(r.edge_k)),
+                     "success_rate": float(ok.mean()), "status_hist": {int(a): int(b) for a, b in zip(*np.unique(st, return_counts=True))},
+                     "iters_mean": float(it.mean()), "iters_max": int(it.max()), "steps": steps,
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_iteration": A_B},
+                     "launch": S.launch_info(), "clocks": summarize_clocks(samples, t_a, t_b)}
+        del mpc, S
+    return out
+
+
+def measure_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE dmb_solve_kernel launch of this workload, from a child process
+    under ncu (two metrics, one replay pass).  Returns (bytes, how)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    try:
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:dmb_solve",
+               "-s", "2", "-c", "1", "--csv", sys.executable, str(ROOT / "bench.py"), "--traffic-child"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        tot = 0.0; n = 0
+        import csv
+        for row in csv.reader(r.stdout.splitlines()):
+            if len(row) > 3 and row[-3].startswith("dram__bytes_"):
+                unit, val = row[-2], float(row[-1].replace(",", ""))
+                tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0); n += 1
+        if n == 2:
+            return tot, "measured in this run: child process under ncu (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    except Exception:
+        pass
+    try:
+        return json.load(open(ROOT / "profiles" / "traffic.json")).get("dram_bytes_per_launch"), "committed capture profiles/traffic.json (ncu could not run here)"
+    except Exception:
+        return None, "unavailable"
+
+
+def traffic_child(B):
+    import torch
+    import cstr
+    x0, up = make_inputs(B, 0)
+    mpc = cstr.cstr_nominal_mpc()
+    r, S = mpc.recipe, mpc.S
+    dev = torch.device("cuda", 0)
+    P, x0s, u0s, _ = mpc.pack_batch(x0, up)
+    dP, dx, du = (torch.tensor(a, device=dev) for a in (P, x0s, u0s))
+    for _ in range(3):
+        S.solve_batch_device(dP, dx, du, None)
+    torch.cuda.synchronize()
 
 
 def main():
@@ -154,7 +262,12 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.traffic_child:
+        return traffic_child(args.batch)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -167,13 +280,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cp = CpuPool(x0, up)
-        cores = cp.cores
-        n_sample = max(cores, min(4 * cores, 512))
-        v, dt, succ = cp.run(n_sample)
+        n_sample = cp.sample_size(B, 20.0)
+        v, dt, succ, ts = cp.run(n_sample)
         cp.close()
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sample} instances (first of the same batch) in {dt:.1f} s, oracle/ipm.py on {cores} processes; "
-                         f"success rate {succ:.2f}; published IPOPT figure for this NLP: 45.6 ms/solve (22 solves/s/core)"}
+        cpu = cpu_baseline_record(cp, v, dt, succ, ts, n_sample, B)
 
     import torch
     import torch.distributed as dist
@@ -186,52 +296,85 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     import cstr
-    from do_mpc_b200.parallel import gather_results
+    from do_mpc_b200.parallel import gather_results, shard_bounds
     mpc = cstr.cstr_nominal_mpc()
     r = mpc.recipe
     S = mpc.S
-    S._set_bounds(mpc._lb_opt_x.full().ravel(), mpc._ub_opt_x.full().ravel())
-    P = np.zeros((B, r.n_p)); P[:, :4] = x0; P[:, 4:6] = up
-    dP = torch.tensor(P, device=dev); dx = torch.tensor(x0 / r.x_scaling, device=dev); du = torch.tensor(up / r.u_scaling, device=dev)
+    P, x0s, u0s, _ = mpc.pack_batch(x0, up)
+    dP, dx, du = (torch.tensor(a, device=dev) for a in (P, x0s, u0s))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
-    out = None
-
-    def step_device():
-        nonlocal out
-        out = S.solve_batch_device(dP, dx, du, None, out=out)
-        if world > 1:
-            return gather_results({k: out[k] for k in ("u0_scaled", "status", "iter_count")}, B * world)
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    def timed(step_fn, total):
+        """W warm-up steps, then K timed steps (CUDA events on the launching stream, L2 flushed before each, barrier +
+        synchronize on both sides); returns (ms per step as max over ranks, kernel ms list)."""
+        for _ in range(args.warmup):
+            step_fn()
+        barrier()
+        evs, kms = [], []
+        for _ in range(args.steps):
+            flush.zero_()                                  # L2 flush between timed iterations (outside the timed events)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_fn(); e1.record()
+            barrier()
+            evs.append(e0.elapsed_time(e1))
+            kms.append(S.launch_info()["last_kernel_ms"])
+        tot = torch.tensor([sum(evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / args.steps, kms
+
     stop = threading.Event(); samples = []
     th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True); th.start()
-    evs = []
+
+    # ---- weak scaling (headline): every rank solves `B` instances ---------------------------------------------------------------
+    out = None
+
+    def step_weak():
+        nonlocal out
+        out = S.solve_batch_device(dP, dx, du, None, out=out)
+        if world > 1:
+            return gather_results({k: out[k] for k in ("u0_scaled", "status", "iter_count")}, B * world)
+        return out
+
     launches0 = S.launch_info()["n_launches"]
-    kernel_ms = []
-    for _ in range(args.steps):
-        flush.zero_()                                  # L2 flush between timed iterations (outside the timed events)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_device()
-        e1.record()
-        barrier()
-        evs.append(e0.elapsed_time(e1))
-        kernel_ms.append(S.launch_info()["last_kernel_ms"])
-    launches = S.launch_info()["n_launches"] - launches0
-    total_ms = torch.tensor([sum(evs)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
+    t_w0 = time.perf_counter()
+    ms_per_step, kernel_ms = timed(step_weak, B * world)
+    t_w1 = time.perf_counter()
+    launches = (S.launch_info()["n_launches"] - launches0) * args.steps // (args.steps + args.warmup)
     value = B * world / (ms_per_step * 1e-3)
+    grid_max = S.launch_info()["grid"]                     # resident CTAs (the persistent grid) when B exceeds them
+    iters = out["iter_count"].cpu().numpy(); status = out["status"].cpu().numpy()
+    st_ = out["stats"].cpu().numpy()
+
+    # ---- strong scaling: the quoted batch (B instances in total) split over the ranks -----------------------------------------------
+    strong = None
+    if world > 1:
+        x0g, upg = make_inputs(B, 0)                       # the rank-0 batch is THE quoted batch; every rank takes its shard of it
+        lo, hi = shard_bounds(B, world, rank)
+        Ps, xs, us, _ = mpc.pack_batch(x0g[lo:hi], upg[lo:hi])
+        dPs, dxs, dus = (torch.tensor(a, device=dev) for a in (Ps, xs, us))
+        outs = None
+
+        def step_strong():
+            nonlocal outs
+            outs = S.solve_batch_device(dPs, dxs, dus, None, out=outs)
+            return gather_results({k: outs[k] for k in ("u0_scaled", "status", "iter_count")}, B)
+
+        ms_s, kms_s = timed(step_strong, B)
+        g = step_strong()
+        it_s = g["iter_count"].cpu().numpy()
+        strong = {"value": B / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s, "global_batch": B, "batch_per_gpu": hi - lo,
+                  "kernel_ms_rank0": float(np.mean(kms_s)),
+                  "resident_ctas_per_gpu": grid_max, "waves_per_gpu": (hi - lo) / max(grid_max, 1),
+                  "iters_mean": float(it_s.mean()), "iters_max": int(it_s.max()),
+                  "limiter": "per-instance latency: one CTA per instance, a step lasts as long as the slowest instance of the last wave "
+                             "(iterations max/mean = %.2f); no collective on the data path" % (it_s.max() / max(it_s.mean(), 1e-9))}
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------------
     for _ in range(2):
@@ -250,9 +393,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / float(te.item())
-    stop.set(); th.join(timeout=2)
 
-    iters = out["iter_count"].cpu().numpy(); status = out["status"].cpu().numpy()
     ok = (status == 0) | (status == 1)
     # ---- roofline of the (single) solve kernel: algorithmic bytes per IPM iteration A_B = 16(3 n_w + n_g) + 8 n_p ------
     A_B = 16 * (3 * r.n_w + r.n_g) + 8 * r.n_p
@@ -264,12 +405,15 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = float(np.mean(kernel_ms))
     achieved = A_B * float(iters.sum() + B) / (k_ms * 1e-3) / 1e9       # +B: the initial point evaluation
-    traffic = None
-    try:
-        traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    st_ = out["stats"].cpu().numpy()
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = run_other_configs(dev, peak, flush, samples)
+    stop.set(); th.join(timeout=2)
+    traffic, traffic_how = (None, "not measured (N > 1 or --no-traffic)")
+    if world == 1 and rank == 0 and not args.no_traffic:
+        del flush
+        torch.cuda.empty_cache()
+        traffic, traffic_how = measure_traffic()
     sub = st_[:, 13:21].sum(axis=0)
     ph = st_[:, 4:13].sum(axis=0)
     phases = {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
@@ -282,21 +426,26 @@ def main():
             "config": {"workload": WORKLOAD.format(B=B), "batch_per_gpu": B, "global_batch": B * world, "n_horizon": r.N,
                        "collocation": "radau deg 2, ni 1", "n_w": r.n_w, "n_g": r.n_g, "parallelism": f"batch-sharded x{world}",
                        "l2": "flushed between timed steps (256 MB write)", "start": "cold (set_initial_guess broadcast)",
+                       "solver": "filter line-search IPM with second-order correction and feasibility restoration",
                        "success_rate": float(ok.mean()), "mean_iters": float(iters.mean()), "max_iters": int(iters.max())},
-            "clocks": summarize_clocks(samples),
+            "clocks": summarize_clocks(samples, t_w0, t_w1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (r.n_p + r.n_x + r.n_u) * 8),
                     "d2h_bytes_per_step": int(B * (r.n_u * 8 + 8 + 4 + 4 + out["stats"].shape[1] * 8))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms,
+                         "traffic": traffic, "traffic_source": traffic_how, "kernel": "dmb_solve_kernel", "kernel_ms": k_ms,
                          **({"phase_share_of_cta_cycles": phases,
                              "subphase_share": {n: round(float(v / max(ph.sum(), 1.0)), 4) for n, v in zip(
                                  ["f_assemble", "f_lu", "f_backsub", "f_mn", "f_reduce", "ric_sweep", "fwd_sweep", "-"], sub)}}
                             if ph.sum() > 0 else {}),
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "note": "algorithmic bytes = A_B(23.3 KB)/IPM iteration x total iterations; iterate state lives in shared memory, "
-                                 "so DRAM traffic is far below this and the kernel is latency/issue bound (DESIGN.md §Roofline)"},
+                         "note": "algorithmic bytes = A_B(23.3 KB)/IPM iteration x total iterations; iterate state lives in shared memory / L2, "
+                                 "so the kernel is latency/issue bound, not DRAM bound (DESIGN.md §5)"},
         }
+        if strong is not None:
+            line["strong"] = strong
+        if other is not None:
+            line["other_configs"] = other
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

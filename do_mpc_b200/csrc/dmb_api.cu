@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_INF_DU] = result.inf_du;
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_OBJ_SCALE] = result.df;
         for (int i = 0; i < DMB_NPHASE; ++i) a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_PHASE0 + i] = (double)result.phase_cycles[i];
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_N_RESTO] = result.n_resto; a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_N_RESTO_IT] = result.n_resto_it;
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_N_SOC] = result.n_soc; a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_N_REFINE] = result.n_refine;
+        a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_N_LS] = result.n_ls;
       }
     }
     __syncthreads();

@@ -230,11 +230,15 @@ DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + 
 // ---------------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------------
+#define DMB_RED_SUM 0
+#define DMB_RED_MAX 1
+#define DMB_RED_MIN 2
 #ifdef DMB_HOSTSIM
 static inline double block_sum(const Ctx&, double v, double*) { return v; }
 static inline double block_max(const Ctx&, double v, double*) { return v; }
 static inline double block_min(const Ctx&, double v, double*) { return v; }
 static inline int group_argmax(const Ctx&, double, int idx) { return idx; }
+template <int NRED> static inline void block_reduce(const Ctx&, double (&)[NRED], const int (&)[NRED], double*) {}
 #else
 #define DMB_FULL 0xffffffffu
 DMB_DEV double warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DMB_FULL, v, o); return v; }
@@ -267,6 +271,29 @@ DMB_DEV double block_min(const Ctx& c, double v, double* scratch) {
   double r = scratch[0];
   for (int i = 1; i < c.nwarp; ++i) r = fmin(r, scratch[i]);
   return r;
+}
+// several reductions behind ONE pair of barriers (the IPM loop reduces ~25 scalars per iteration; one block_sum / block_max
+// each cost two barriers apiece).  op[k]: 0 = sum, 1 = max, 2 = min.  Same shuffle tree and same order over the warps as
+// block_sum / block_max / block_min, so the results are bit-identical to the separate calls.  Result broadcast in v[].
+// scratch: >= NV * nwarp doubles.
+template <int NRED>
+DMB_DEV void block_reduce(const Ctx& c, double (&v)[NRED], const int (&op)[NRED], double* scratch) {
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) v[k] = op[k] == DMB_RED_SUM ? warp_sum(v[k]) : (op[k] == DMB_RED_MAX ? warp_max(v[k]) : warp_min(v[k]));
+  CTA_SYNC();
+  if (c.lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) scratch[k * c.nwarp + c.warp] = v[k];
+  }
+  CTA_SYNC();
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    double r = scratch[k * c.nwarp];
+    if (op[k] == DMB_RED_SUM) { r = 0.0; for (int i = 0; i < c.nwarp; ++i) r += scratch[k * c.nwarp + i]; }
+    else if (op[k] == DMB_RED_MAX) for (int i = 1; i < c.nwarp; ++i) r = fmax(r, scratch[k * c.nwarp + i]);
+    else for (int i = 1; i < c.nwarp; ++i) r = fmin(r, scratch[k * c.nwarp + i]);
+    v[k] = r;
+  }
 }
 // index of the largest |val| among the lanes of a group (idx < 64, idx < 0 = no candidate): one REDUX on packed keys
 DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
@@ -333,8 +360,28 @@ DMB_DEV double nl_ub_relaxed(const Inst& I, int e, int i) {
 // residuals + objective at a point (w, s) -> res (scaled), objective (scaled by df), theta = ||res||_1.
 // One thread per edge for the generated code; all threads for the reductions.
 // ---------------------------------------------------------------------------------------------------
+// per-thread partial sums of the barrier terms of a point: acc += -mu log(slack) (+ kappa_d mu slack for one-sided bounds),
+// bad = 1 outside the bounds
+DMB_DEV void barrier_terms(const Ctx& c, const Inst& I, const double* w, const double* s, double mu, double kappa_d, double& acc, double& bad) {
+  for (int i = c.tid; i < NWI; i += c.nthr) {
+    const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
+    if (hl) { const double sl = w[i] - I.lb[i]; if (sl <= 0.0) bad = 1.0; else { acc -= mu * log(sl); if (!hu) acc += kappa_d * mu * sl; } }
+    if (hu) { const double su = I.ub[i] - w[i]; if (su <= 0.0) bad = 1.0; else { acc -= mu * log(su); if (!hl) acc += kappa_d * mu * su; } }
+  }
+#if NNL > 0
+  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
+    const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - s[i];
+    if (su <= 0.0) bad = 1.0; else acc += -mu * log(su) + kappa_d * mu * su;
+  }
+#else
+  (void)s;
+#endif
+}
+
+// phi_out != nullptr (and phi_mu >= 0): also the barrier function phi_mu(w, s) = f + barrier terms, in the same reduction
 DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const double* s, double* res,
-                        double* scratch, double* f_out, double* theta_out, double* infpr_out) {
+                        double* scratch, double* f_out, double* theta_out, double* infpr_out,
+                        double phi_mu = -1.0, double phi_kappa_d = 0.0, double* phi_out = nullptr) {
   double f = 0.0;
   for (int e = c.tid; e < NEDGE; e += c.nthr) {
     double q[NQ], g[NY > 0 ? NY : 1];
@@ -371,9 +418,14 @@ DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const do
   CTA_SYNC();
   double th = 0.0, mx = 0.0;
   for (int i = c.tid; i < NLAM; i += c.nthr) { const double a = fabs(res[i]); th += a; mx = fmax(mx, a); }
-  *f_out = I.df * block_sum(c, f, scratch);
-  *theta_out = block_sum(c, th, scratch);
-  if (infpr_out) *infpr_out = block_max(c, mx, scratch);
+  double v[5] = {f, th, mx, 0.0, 0.0};
+  if (phi_mu >= 0.0) barrier_terms(c, I, w, s, phi_mu, phi_kappa_d, v[3], v[4]);
+  const int op[5] = {DMB_RED_SUM, DMB_RED_SUM, DMB_RED_MAX, DMB_RED_SUM, DMB_RED_MAX};
+  block_reduce<5>(c, v, op, scratch);
+  *f_out = I.df * v[0];
+  *theta_out = v[1];
+  if (infpr_out) *infpr_out = v[2];
+  if (phi_out) *phi_out = v[4] > 0.0 ? INFINITY : *f_out + v[3];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -382,6 +434,9 @@ DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const do
 // objective (go) and of the Lagrangian without bound multipliers (gl) for every primal variable.
 // lam are the SCALED multipliers; the row scales dc are applied here.
 // ---------------------------------------------------------------------------------------------------
+// (measured and rejected in round 2: splitting the generated function into 4 parts evaluated by 4 warps — the expensive
+//  sub-expressions (exp / division of the Arrhenius terms) are shared by all outputs and were recomputed per part:
+//  cfg #2 34.4 ms with the split against 32.3 ms without, gpurun_out/r2e_quick.json / r2f_quick.json)
 DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
   const double* w = I.w;
   for (int e = c.tid; e < NEDGE; e += c.nthr) {
@@ -396,12 +451,6 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
     double* eb = I.eb + (size_t)e * EB_SZ;
     gen_derivs(q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln,
                eb + EB_GOBJ, eb + EB_GCON, eb + EB_JNZ, eb + EB_HNZ, eb + EB_DNZ);
-    // continuity multiplier on the end-of-interval state, inequality Jacobian scaling
-#pragma unroll
-    for (int i = 0; i < NX; ++i) eb[EB_GCON + NVP + DMB_XF_SEL[i]] += le[NY + i];
-#if NNL > 0
-    for (int k = 0; k < DMB_NNZ_D; ++k) eb[EB_DNZ + k] *= dc[NY + NX + DMB_D_ROW[k]];
-#endif
   }
   // weighted rterm derivatives per node (reference _mpc.py:1263-1275), used by the gradients below and the sweep
   for (int n = c.nthr - 1 - c.tid; n < NNODE; n += c.nthr) {
@@ -460,8 +509,17 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
     const double* eb = I.eb + (size_t)e * EB_SZ;
     const double go = eb[EB_GOBJ + NVP + i];
     if (!I.resto) I.go[NNODE * NVP + idx] = go;
-    I.gl[NNODE * NVP + idx] = go + eb[EB_GCON + NVP + i];
+    // constraint part + continuity multiplier on the end-of-interval state (same association as the former in-place update)
+    const double gcon = DMB_XF_INV[i] >= 0 ? eb[EB_GCON + NVP + i] + I.lam[LAM_EDGE(e) + NY + DMB_XF_INV[i]] : eb[EB_GCON + NVP + i];
+    I.gl[NNODE * NVP + idx] = go + gcon;
   }
+#if NNL > 0
+  // inequality Jacobian nonzeros: row scaling
+  for (int idx = c.tid; idx < NEDGE * DMB_NNZ_D; idx += c.nthr) {
+    const int e = idx / DMB_NNZ_D, k = idx - e * DMB_NNZ_D;
+    I.eb[(size_t)e * EB_SZ + EB_DNZ + k] *= I.dc[LAM_EDGE(e) + NY + NX + DMB_D_ROW[k]];
+  }
+#endif
   CTA_SYNC();
 }
 

@@ -9,7 +9,7 @@
 static int dmb_hostsim_verbose = 0;
 #endif
 struct DmbShared {          // small per-CTA state in shared memory
-  double red[40];           // reduction scratch
+  double red[64];           // reduction scratch (block_reduce: values x warps)
   double filt_theta[MAX_FILTER], filt_phi[MAX_FILTER];
   int n_filt;
   int flag, fail;
@@ -18,7 +18,7 @@ struct DmbShared {          // small per-CTA state in shared memory
 #define DMB_NPHASE 17
 struct DmbResult {
   double f, mu, inf_pr, inf_du, df;
-  int status, iters, n_resto;
+  int status, iters, n_resto, n_resto_it, n_soc, n_refine, n_ls;
   long long phase_cycles[DMB_NPHASE];   // derivs | kkt+mu | factor | riccati | forward+recover | step sizes | line search | accept | init
 };
 #ifdef DMB_PROFILE
@@ -34,32 +34,24 @@ DMB_DEV double ftb_step(double slack, double dslack, double tau) {   // largest 
 // barrier function value given objective f (scaled); returns +inf outside the bounds
 DMB_DEV double barrier_phi(const Ctx& c, const Inst& I, const double* w, const double* s, double mu, double kappa_d,
                            double f, double* red) {
-  double acc = 0.0; double bad = 0.0;
-  for (int i = c.tid; i < NWI; i += c.nthr) {
-    const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
-    if (hl) { const double sl = w[i] - I.lb[i]; if (sl <= 0.0) bad = 1.0; else { acc -= mu * log(sl); if (!hu) acc += kappa_d * mu * sl; } }
-    if (hu) { const double su = I.ub[i] - w[i]; if (su <= 0.0) bad = 1.0; else { acc -= mu * log(su); if (!hl) acc += kappa_d * mu * su; } }
-  }
-#if NNL > 0
-  for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
-    const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - s[i];
-    if (su <= 0.0) bad = 1.0; else acc += -mu * log(su) + kappa_d * mu * su;
-  }
-#endif
-  const double b = block_max(c, bad, red);
-  const double a = block_sum(c, acc, red);
-  return b > 0.0 ? INFINITY : f + a;
+  double v[2] = {0.0, 0.0};
+  barrier_terms(c, I, w, s, mu, kappa_d, v[0], v[1]);
+  const int op[2] = {DMB_RED_SUM, DMB_RED_MAX};
+  block_reduce<2>(c, v, op, red);
+  return v[1] > 0.0 ? INFINITY : f + v[0];
 }
 
-// optimality error pieces for a given mu: dual infeasibility uses gl = grad L (without z), then -zL+zU
+// optimality error pieces in ONE pass and one reduction: dual infeasibility (gl = grad L without z, then -zL+zU),
+// complementarity for the barrier parameter mu AND for mu = 0, the scaling factors s_d, s_c, and the unscaled primal
+// infeasibility max |res| / dc
 DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, double* red,
-                       double* dual, double* compl_, double* s_d, double* s_c) {
-  double du = 0.0, cm = 0.0, sz = 0.0, nz = 0.0, sy = 0.0;
+                       double* dual, double* compl_mu, double* compl_0, double* s_d, double* s_c, double* prim_unscaled) {
+  double du = 0.0, cm = 0.0, c0 = 0.0, sz = 0.0, nz = 0.0, sy = 0.0, pu = 0.0;
   for (int i = c.tid; i < NWI; i += c.nthr) {
     const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
     double r = I.gl[i];
-    if (hl) { r -= I.zL[i]; cm = fmax(cm, fabs((I.w[i] - I.lb[i]) * I.zL[i] - mu)); sz += fabs(I.zL[i]); nz += 1.0; }
-    if (hu) { r += I.zU[i]; cm = fmax(cm, fabs((I.ub[i] - I.w[i]) * I.zU[i] - mu)); sz += fabs(I.zU[i]); nz += 1.0; }
+    if (hl) { const double sz_ = (I.w[i] - I.lb[i]) * I.zL[i]; r -= I.zL[i]; cm = fmax(cm, fabs(sz_ - mu)); c0 = fmax(c0, fabs(sz_)); sz += fabs(I.zL[i]); nz += 1.0; }
+    if (hu) { const double sz_ = (I.ub[i] - I.w[i]) * I.zU[i]; r += I.zU[i]; cm = fmax(cm, fabs(sz_ - mu)); c0 = fmax(c0, fabs(sz_)); sz += fabs(I.zU[i]); nz += 1.0; }
     du = fmax(du, fabs(r));
   }
 #if NNL > 0
@@ -67,17 +59,19 @@ DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, dou
     const int e = i / NNL, j = i % NNL;
     const double yd = I.lam[LAM_EDGE(e) + NY + NX + j];
     du = fmax(du, fabs(-yd + I.vU[i]));
-    cm = fmax(cm, fabs((nl_ub_relaxed(I, e, j) - I.s[i]) * I.vU[i] - mu));
+    const double sv = (nl_ub_relaxed(I, e, j) - I.s[i]) * I.vU[i];
+    cm = fmax(cm, fabs(sv - mu)); c0 = fmax(c0, fabs(sv));
     sz += fabs(I.vU[i]); nz += 1.0;
   }
 #endif
-  for (int i = c.tid; i < NLAM; i += c.nthr) sy += fabs(I.lam[i]);
-  *dual = block_max(c, du, red);
-  *compl_ = block_max(c, cm, red);
-  const double SZ = block_sum(c, sz, red), NZ = block_sum(c, nz, red), SY = block_sum(c, sy, red);
+  for (int i = c.tid; i < NLAM; i += c.nthr) { sy += fabs(I.lam[i]); pu = fmax(pu, fabs(I.res[i]) / I.dc[i]); }
+  double v[7] = {du, cm, c0, sz, nz, sy, pu};
+  const int op[7] = {DMB_RED_MAX, DMB_RED_MAX, DMB_RED_MAX, DMB_RED_SUM, DMB_RED_SUM, DMB_RED_SUM, DMB_RED_MAX};
+  block_reduce<7>(c, v, op, red);
+  *dual = v[0]; *compl_mu = v[1]; *compl_0 = v[2]; *prim_unscaled = v[6];
   const double m_tot = (double)NLAM_ACTIVE;
-  *s_d = fmax(s_max, (SY + SZ) / fmax(m_tot + NZ, 1.0)) / s_max;
-  *s_c = fmax(s_max, SZ / fmax(NZ, 1.0)) / s_max;
+  *s_d = fmax(s_max, (v[5] + v[3]) / fmax(m_tot + v[4], 1.0)) / s_max;
+  *s_c = fmax(s_max, v[3] / fmax(v[4], 1.0)) / s_max;
 }
 
 // ---- cold-path helpers: ONE out-of-line copy each, shared by the starting point, the second-order correction and the
@@ -87,21 +81,18 @@ DMB_DEV void kkt_error(const Ctx& c, const Inst& I, double mu, double s_max, dou
 #else
 #define DMB_COLD __device__ __noinline__
 #endif
-DMB_COLD void eval_point_cold(const Ctx& c, const Inst& I, const double* w, const double* s, double* res, double* scratch,
+// (arguments BY VALUE: the caller's Ctx / Inst never have their address taken, so they stay in registers in the hot loop)
+DMB_COLD void eval_point_cold(const Ctx c, const Inst I, const double* w, const double* s, double* res, double* scratch,
                               double* f_out, double* theta_out, double* infpr_out) {
   eval_point(c, I, w, s, res, scratch, f_out, theta_out, infpr_out);
 }
 // K [dw; lam+; ds] = -[rd; rp] with the factors of the current iteration: rd = I.gl, rp = I.rest  ->  I.dw, I.lamn, I.ds
-#ifdef DMB_RESOLVE_INLINE
-DMB_DEV
-#else
-DMB_COLD
-#endif
-void resolve_system(const Ctx& c, const Inst& I, double delta_w, double* tile, double* Qs) {
+DMB_DEV void resolve_system(const Ctx& c, const Inst& I, double delta_w, double* tile, double* Qs) {
   resolve_edges(c, I, tile);
   riccati_vector(c, I, delta_w, Qs);
   forward_recover(c, I, I.rest, delta_w, 0, 1, tile);
 }
+DMB_COLD void resolve_system_cold(const Ctx c, const Inst I, double delta_w, double* tile, double* Qs) { resolve_system(c, I, delta_w, tile, Qs); }
 
 // filter acceptance test of a trial point (Waechter & Biegler 2006, Sec. 2.3): 0 = rejected, 1 = accepted (the filter gets
 // augmented), 2 = accepted under the Armijo condition
@@ -190,7 +181,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
   double theta_max = 0.0, theta_min = 0.0;
   double delta_w_last = 0.0;
-  int it = 0, status = DMB_MAXIMUM_ITERATIONS_EXCEEDED, acceptable_cnt = 0, n_resto = 0;
+  int it = 0, status = DMB_MAXIMUM_ITERATIONS_EXCEEDED, acceptable_cnt = 0, n_resto = 0, n_resto_it = 0, n_soc = 0, n_refine = 0, n_ls = 0;
   const int degenerate_reg = o.mimic_dummy_reg && DMB_HAS_DUMMIES;
   bool acceptable_now = false;
   double dual0 = 0.0;
@@ -290,8 +281,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     DMB_TICK(0);
     if (mode == MODE_NORMAL) {
       // ---- convergence tests ----------------------------------------------------------------------------------------------
-      double dual, cmpl, s_d, s_c;
-      kkt_error(c, I, 0.0, o.s_max, red, &dual, &cmpl, &s_d, &s_c);
+      double dual, cmpl_mu, cmpl, s_d, s_c, pu;
+      kkt_error(c, I, mu, o.s_max, red, &dual, &cmpl_mu, &cmpl, &s_d, &s_c, &pu);
       dual0 = dual;
       const double E0 = fmax(fmax(dual / s_d, inf_pr), cmpl / s_c);
 #ifdef DMB_HOSTSIM
@@ -299,9 +290,6 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
 #endif
       {
         // unscaled secondary tolerances
-        double pu = 0.0;
-        for (int i = c.tid; i < NLAM; i += c.nthr) pu = fmax(pu, fabs(I.res[i]) / I.dc[i]);
-        pu = block_max(c, pu, red);
         const double du_u = dual / I.df, cm_u = cmpl / I.df;
         if (!(E0 == E0)) { status = DMB_INVALID_NUMBER_DETECTED; break; }
         if (E0 <= o.tol && du_u <= o.dual_inf_tol && pu <= o.constr_viol_tol && cm_u <= o.compl_inf_tol) { status = DMB_SOLVE_SUCCEEDED; break; }
@@ -311,11 +299,9 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
         } else acceptable_cnt = 0;
         if (it >= o.max_iter) { status = DMB_MAXIMUM_ITERATIONS_EXCEEDED; break; }
       }
-      // ---- barrier parameter (monotone, repeated decrease allowed) ----------------------------------------------------
+      // ---- barrier parameter (monotone, repeated decrease allowed); the first test re-uses the pass above ----------------
       while (true) {
-        double dm, cmm, sd2, sc2;
-        kkt_error(c, I, mu, o.s_max, red, &dm, &cmm, &sd2, &sc2);
-        const double Emu = fmax(fmax(dm / sd2, inf_pr), cmm / sc2);
+        const double Emu = fmax(fmax(dual / s_d, inf_pr), cmpl_mu / s_c);
         if (Emu <= o.kappa_eps * mu && mu > o.mu_min) {
           double nm = fmax(o.tol / 10.0, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
           nm = fmax(nm, o.mu_min);
@@ -323,6 +309,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
           mu = nm; tau = fmax(o.tau_min, 1.0 - mu);
           if (c.tid == 0) S->n_filt = 0;
           CTA_SYNC();
+          double c0_;
+          kkt_error(c, I, mu, o.s_max, red, &dual, &cmpl_mu, &c0_, &s_d, &s_c, &pu);
         } else break;
       }
     }
@@ -406,6 +394,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
             if (okf) for (int k = 0; k < S->n_filt; ++k) if (!(theta < S->filt_theta[k] || phi_t < S->filt_phi[k])) { okf = false; break; }
             if (okf) { leave = true; success = true; f = f_t; }
           }
+          ++n_resto_it;
           if (!leave && ++resto_it >= o.resto_max_iter) leave = true;
         }
       }
@@ -443,6 +432,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       for (int i = c.tid; i < NLAM; i += c.nthr) I.lamr[i] = I.lamn[i];
       for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.ds[i];
       CTA_SYNC();
+      ++n_refine;
       resolve_system(c, I, delta_w, tile, Qs);
       for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];
       for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] += I.lamr[i];
@@ -483,10 +473,15 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       dphi += (mu / su - o.kappa_d * mu) * d;
     }
 #endif
-    a_max = block_min(c, a_max, red);
-    a_z = block_min(c, a_z, red);
-    dphi = block_sum(c, dphi, red);
-    const double phi = barrier_phi(c, I, I.w, I.s, mu, o.kappa_d, f, red);
+    double phi;
+    {
+      double v[5] = {a_max, a_z, dphi, 0.0, 0.0};
+      barrier_terms(c, I, I.w, I.s, mu, o.kappa_d, v[3], v[4]);
+      const int op[5] = {DMB_RED_MIN, DMB_RED_MIN, DMB_RED_SUM, DMB_RED_SUM, DMB_RED_MAX};
+      block_reduce<5>(c, v, op, red);
+      a_max = v[0]; a_z = v[1]; dphi = v[2];
+      phi = v[4] > 0.0 ? INFINITY : f + v[3];
+    }
     DMB_TICK(5);
 
     // ---- filter line search -------------------------------------------------------------------------------------------------
@@ -501,12 +496,12 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
     double f_t = f, theta_t = theta, infpr_t = inf_pr;
     int ls = 0;
     while (alpha >= a_min || ls == 0) {
-      ++ls;
+      ++ls; ++n_ls;
       for (int i = c.tid; i < NWI; i += c.nthr) I.wt[i] = I.w[i] + alpha * I.dw[i];
       for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.s[i] + alpha * I.ds[i];
       CTA_SYNC();
-      eval_point(c, I, I.wt, I.st, I.rest, red, &f_t, &theta_t, &infpr_t);
-      const double phi_t = barrier_phi(c, I, I.wt, I.st, mu, o.kappa_d, f_t, red);
+      double phi_t;
+      eval_point(c, I, I.wt, I.st, I.rest, red, &f_t, &theta_t, &infpr_t, mu, o.kappa_d, &phi_t);
       const int acc = trial_acceptable(o, S, theta_t, phi_t, theta, phi, dphi, alpha, theta_max, theta_min);
       if (acc) { accepted = true; armijo = acc == 2; a_used = alpha; break; }
       // ---- second-order correction on the first trial when the infeasibility did not decrease (W&B 2006, Sec. 2.4) -------------
@@ -519,7 +514,8 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
         CTA_SYNC();
         double theta_old = theta_t;
         for (int soc_it = 0; soc_it < o.max_soc; ++soc_it) {
-          resolve_system(c, I, delta_w, tile, Qs);
+          ++n_soc;
+          resolve_system_cold(c, I, delta_w, tile, Qs);
           for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];
           for (int i = c.tid; i < NLAM; i += c.nthr) I.lamn[i] += I.lamr[i];
           for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.ds[i] += I.st[i];
@@ -628,6 +624,7 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
   if (c.tid == 0) {
     out->f = f / I.df; out->mu = mu; out->inf_pr = inf_pr; out->inf_du = dual0;
     out->status = status; out->iters = it; out->n_resto = n_resto; out->df = I.df;
+    out->n_resto_it = n_resto_it; out->n_soc = n_soc; out->n_refine = n_refine; out->n_ls = n_ls;
 #ifdef DMB_PROFILE
     for (int i = 0; i < DMB_NPHASE; ++i) out->phase_cycles[i] = pc[i];
 #else

@@ -23,7 +23,11 @@ _STATUS_NAMES = {0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", 2: "Infe
                  -13: "Invalid_Number_Detected", -100: "Not_Run"}
 (DIM_NW, DIM_NG, DIM_NP, DIM_NX, DIM_NU, DIM_NZ, DIM_NAUX, DIM_NHOR, DIM_NSCEN, DIM_NEDGE, DIM_NNODE, DIM_OPTSIZE,
  DIM_THREADS, DIM_SMEM, DIM_WS, DIM_COUNT) = range(16)
-NSTAT = 21
+NSTAT = 26
+import os as _os
+if "DMB_NSTAT" in _os.environ:          # A/B experiments against an older kernel source (21 statistics per instance)
+    NSTAT = int(_os.environ["DMB_NSTAT"])
+STAT_N_RESTO, STAT_N_RESTO_IT, STAT_N_SOC, STAT_N_REFINE, STAT_N_LS = 21, 22, 23, 24, 25
 PHASE_NAMES = ['derivs', 'kkt+mu', 'factor', 'riccati', 'forward+recover', 'stepsize', 'linesearch', 'accept', 'init']
 
 _c_dp = ctypes.c_void_p

@@ -18,8 +18,8 @@ from ..recipe import Recipe
 from .codegen import generate
 
 PKG = Path(__file__).resolve().parent.parent
-CSRC = PKG / "csrc"
-INCLUDE = PKG.parent / "include"
+CSRC = Path(os.environ.get("DMB_CSRC_DIR", PKG / "csrc"))              # override: A/B experiments against an older kernel source
+INCLUDE = Path(os.environ.get("DMB_INCLUDE_DIR", PKG.parent / "include"))
 CACHE = PKG / "_kcache"
 NVCC = os.environ.get("NVCC", shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -115,9 +115,9 @@ def generate(r: Recipe) -> str:
     fused = ([(f"gobj[{i}]", e) for i, e in enumerate(gO)] + [(f"gcon[{i}]", e) for i, e in enumerate(gC)] +
              [(f"jnz[{k}]", e) for k, e in enumerate(jn)] + [(f"hnz[{k}]", e) for k, e in enumerate(hn)] +
              [(f"dnz[{k}]", e) for k, e in enumerate(dn)])
-    out.append(_fn("gen_derivs", lag_args + ", double* __restrict__ gobj, double* __restrict__ gcon, double* __restrict__ jnz, "
-                   "double* __restrict__ hnz, double* __restrict__ dnz",
-                   "  (void)lam; (void)lnl; (void)hnz; (void)dnz;\n" + E.emit_c(fused, inpL)))
+    d_args = lag_args + ", double* __restrict__ gobj, double* __restrict__ gcon, double* __restrict__ jnz, double* __restrict__ hnz, double* __restrict__ dnz"
+    d_void = "  (void)q; (void)tvp; (void)pp; (void)lam; (void)lnl; (void)sig_l; (void)sig_e; (void)gobj; (void)gcon; (void)jnz; (void)hnz; (void)dnz;\n"
+    out.append(_fn("gen_derivs", d_args, d_void + E.emit_c(fused, inpL)))
     # row-wise (CSR) views: J rows (nonzeros are emitted row-major), full symmetric H rows
     jr_start = [0] * (len(G_ids) + 1)
     for r_ in jr: jr_start[r_ + 1] += 1
@@ -244,6 +244,9 @@ def generate(r: Recipe) -> str:
     H.append(_ctab("int", "DMB_EDGE_YX_FLAT", r.edge_yx_flat)); H.append(_ctab("int", "DMB_EDGE_YZ_FLAT", r.edge_yz_flat))
     H.append(_ctab("int", "DMB_EDGE_G_FLAT", r.edge_g_flat))
     H.append(_ctab("int", "DMB_XF_SEL", r.xf_sel))
+    xf_inv = [-1] * r.n_y
+    for a_, j_ in enumerate(r.xf_sel): xf_inv[int(j_)] = a_
+    H.append(_ctab("int", "DMB_XF_INV", xf_inv))
     S_ = r.n_comb ** r.n_robust
     ks_node = []
     for k in range(r.N):

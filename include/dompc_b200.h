@@ -51,7 +51,10 @@ enum { DMB_DIM_NW = 0, DMB_DIM_NG, DMB_DIM_NP, DMB_DIM_NX, DMB_DIM_NU, DMB_DIM_N
 
 /* per-instance statistics written by the solve calls: stats[b*DMB_NSTAT + k] */
 enum { DMB_STAT_MU = 0, DMB_STAT_INF_PR, DMB_STAT_INF_DU, DMB_STAT_OBJ_SCALE,
-       DMB_STAT_PHASE0 /* 9 + 8 SM-clock cycle counters of the solver (sub)phases, see DmbResult */, DMB_NSTAT = DMB_STAT_PHASE0 + 17 };
+       DMB_STAT_PHASE0 /* 9 + 8 SM-clock cycle counters of the solver (sub)phases, see DmbResult */,
+       DMB_STAT_N_RESTO = DMB_STAT_PHASE0 + 17 /* restoration phases entered */, DMB_STAT_N_RESTO_IT /* restoration iterations */,
+       DMB_STAT_N_SOC /* second-order-correction solves */, DMB_STAT_N_REFINE /* iterative-refinement solves */,
+       DMB_STAT_N_LS /* line-search trial points */, DMB_NSTAT };
 
 typedef struct dmb_solver dmb_solver;
 struct DmbOptions;   /* layout: do_mpc_b200/csrc/ipm_core.cuh, mirrored by do_mpc_b200/solver/options.py */

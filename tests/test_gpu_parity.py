@@ -32,7 +32,7 @@ def test_full_solution_kkt_and_oracle(mpc, dataset):
     used = nlp.used_mask()
     idx = np.where(dataset["success"])[0][:6]
     out = mpc.make_step_batch(dataset["x0"][idx], dataset["u_prev"][idx], return_full=True)
-    orc = IPMSolver(nlp, IpmOptions(max_iter=300, max_soc=0))
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
     for b, i in enumerate(idx):
         p = nlp.pack_p(dataset["x0"][i], dataset["u_prev"][i])
         x, lam_g, lam_x = out["x"][b], out["lam_g"][b], out["lam_x"][b]

@@ -58,7 +58,7 @@ def test_full_solution_is_kkt_point_of_oracle_nlp(sim, dataset):
 def test_matches_oracle_iterates(sim, dataset):
     """Same algorithm, different linear algebra (stage elimination vs dense LDL^T): solutions agree to 1e-9."""
     nlp = FlatNLP(models.cstr_nominal())
-    orc = IPMSolver(nlp, IpmOptions(max_iter=300, max_soc=0))
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
     idx = [0, 1, 3, 7, 11]
     P, x0s, u0s = cstr_batch_inputs(sim.r, dataset["x0"][idx], dataset["u_prev"][idx])
     out = sim.solve(P, x0s, u0s)
