@@ -180,7 +180,7 @@ __global__ void dmb_aux_kernel(int B, const double* x, const double* p, double* 
     const int b = (int)(idx / per), ks = (int)(idx % per);
     // node (k, s); scenario slots beyond the populated ones repeat the last one (reference _mpc.py:1282-1284)
     const int n = DMB_KS_NODE[ks];
-    const int e = DMB_NODE_FIRST_EDGE[n] + DMB_NODE_NEDGE[n] - 1;
+    const int e = NODE_FIRST_EDGE(n) + NODE_NEDGE(n) - 1;
     const double* xb = x + (size_t)b * DMB_NW;
     const double* pb = p + (size_t)b * DMB_NP;
     double q[NQ], a[DMB_NAUX > 0 ? DMB_NAUX : 1];

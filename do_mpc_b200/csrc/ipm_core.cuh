@@ -72,6 +72,32 @@ enum DmbStatus {
 
 #include "problem_gen.h"   // generated: dimensions, tables, model functions
 
+// tree topology of nodes / edges.  Chains (one scenario) need no table loads — node n is stage n with the single edge n to
+// node n + 1 — which takes dependent global loads out of every sweep (r1e capture: 14 % of the sweep's stalls).
+#if DMB_NSCEN > 1
+#define NODE_NEDGE(n) DMB_NODE_NEDGE[n]
+#define NODE_FIRST_EDGE(n) DMB_NODE_FIRST_EDGE[n]
+#define EDGE_CHILD_OF(e) DMB_EDGE_CHILD[e]
+#define EDGE_PARENT_OF(e) DMB_EDGE_PARENT[e]
+#define NODE_PARENT_EDGE(n) DMB_NODE_PARENT_EDGE[n]
+#define NODE_K_OF(n) DMB_NODE_K[n]
+#define EDGE_K_OF(e) DMB_EDGE_K[e]
+#define EDGE_PIDX_OF(e) DMB_EDGE_PIDX[e]
+#define EDGE_OMEGA_OF(e) DMB_EDGE_OMEGA[e]
+#define NODE_RW_OF(n) DMB_NODE_RW[n]
+#else
+#define NODE_NEDGE(n) ((n) < DMB_NHOR ? 1 : 0)
+#define NODE_FIRST_EDGE(n) (n)
+#define EDGE_CHILD_OF(e) ((e) + 1)
+#define EDGE_PARENT_OF(e) (e)
+#define NODE_PARENT_EDGE(n) ((n) - 1)
+#define NODE_K_OF(n) (n)
+#define EDGE_K_OF(e) (e)
+#define EDGE_PIDX_OF(e) 0
+#define EDGE_OMEGA_OF(e) 1.0
+#define NODE_RW_OF(n) ((n) < DMB_NHOR ? 1.0 : 0.0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // derived dimensions and layouts
 // ---------------------------------------------------------------------------------------------------
@@ -331,21 +357,21 @@ DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
 // gather of the edge-local vector q = (x_parent, u_parent, eps_parent, y_e) and its parameters
 // ---------------------------------------------------------------------------------------------------
 DMB_DEV void gather_q(const double* w, int e, double* q) {
-  const double* wn = w + NODE_OFF(DMB_EDGE_PARENT[e]);
+  const double* wn = w + NODE_OFF(EDGE_PARENT_OF(e));
 #pragma unroll
   for (int i = 0; i < NVP; ++i) q[i] = wn[i];
   const double* wy = w + EDGE_OFF(e);
 #pragma unroll
   for (int i = 0; i < NY; ++i) q[NVP + i] = wy[i];
 }
-DMB_DEV const double* edge_tvp(const double* p, int e) { return p + DMB_P_TVP + DMB_EDGE_K[e] * DMB_NTVP; }
-DMB_DEV const double* edge_pp(const double* p, int e) { return p + DMB_P_P + DMB_EDGE_PIDX[e] * DMB_NPM; }
+DMB_DEV const double* edge_tvp(const double* p, int e) { return p + DMB_P_TVP + EDGE_K_OF(e) * DMB_NTVP; }
+DMB_DEV const double* edge_pp(const double* p, int e) { return p + DMB_P_P + EDGE_PIDX_OF(e) * DMB_NPM; }
 
 // u_prev (scaled) seen by node n: the parent's input, or the parameter for the root (reference _mpc.py:1273)
 DMB_DEV double node_uprev(const Inst& I, const double* w, int n, int i) {
-  const int pe = DMB_NODE_PARENT_EDGE[n];
+  const int pe = NODE_PARENT_EDGE(n);
   if (pe < 0) return I.p[DMB_P_UPREV + i] * DMB_INV_USCALE[i];
-  return w[NODE_OFF(DMB_EDGE_PARENT[pe]) + NX + i];
+  return w[NODE_OFF(EDGE_PARENT_OF(pe)) + NX + i];
 }
 
 #if DMB_NNL > 0
@@ -393,7 +419,7 @@ DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const do
     const double* dc = I.dc + LAM_EDGE(e);
 #pragma unroll
     for (int i = 0; i < NY; ++i) r[i] = dc[i] * g[i];
-    const double* xc = w + NODE_OFF(DMB_EDGE_CHILD[e]);
+    const double* xc = w + NODE_OFF(EDGE_CHILD_OF(e));
 #pragma unroll
     for (int i = 0; i < NX; ++i) r[NY + i] = q[NVP + DMB_XF_SEL[i]] - xc[i];
 #if NNL > 0
@@ -404,15 +430,15 @@ DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const do
 #endif
     double lt, ec;
     gen_cost(q, tv, pp, &lt, &ec);
-    f += DMB_EDGE_OMEGA[e] * lt + ec;
-    if (DMB_EDGE_K[e] == NHOR - 1) f += DMB_EDGE_OMEGA[e] * gen_mterm(xc, p_tvp_at(I.p, NHOR), pp);
+    f += EDGE_OMEGA_OF(e) * lt + ec;
+    if (EDGE_K_OF(e) == NHOR - 1) f += EDGE_OMEGA_OF(e) * gen_mterm(xc, p_tvp_at(I.p, NHOR), pp);
   }
   for (int n = c.tid; n < NNODE; n += c.nthr) {
-    if (DMB_NODE_K[n] == NHOR) continue;
+    if (NODE_K_OF(n) == NHOR) continue;
     double up[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) up[i] = node_uprev(I, w, n, i);
-    f += DMB_NODE_RW[n] * gen_rterm(w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + DMB_NODE_K[n] * DMB_NTVP);
+    f += NODE_RW_OF(n) * gen_rterm(w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + NODE_K_OF(n) * DMB_NTVP);
   }
   for (int i = c.tid; i < NX; i += c.nthr) res[i] = w[NODE_OFF(0) + i] - I.p[DMB_P_X0 + i] * DMB_INV_XSCALE[i];
   CTA_SYNC();
@@ -449,13 +475,13 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
 #pragma unroll
     for (int i = 0; i < NNL; ++i) ln[i] = dc[NY + NX + i] * le[NY + NX + i];
     double* eb = I.eb + (size_t)e * EB_SZ;
-    gen_derivs(q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, I.df * DMB_EDGE_OMEGA[e], I.df, ln,
+    gen_derivs(q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, I.df * EDGE_OMEGA_OF(e), I.df, ln,
                eb + EB_GOBJ, eb + EB_GCON, eb + EB_JNZ, eb + EB_HNZ, eb + EB_DNZ);
   }
   // weighted rterm derivatives per node (reference _mpc.py:1263-1275), used by the gradients below and the sweep
   for (int n = c.nthr - 1 - c.tid; n < NNODE; n += c.nthr) {
     double* wn = I.node + (size_t)n * WN_NODE;
-    const int k = DMB_NODE_K[n];
+    const int k = NODE_K_OF(n);
     if (k == NHOR) continue;
     double up[NU], gr[2 * NU], hr[4 * NU * NU];
 #pragma unroll
@@ -463,7 +489,7 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
     const double* tv = I.p + DMB_P_TVP + k * DMB_NTVP;
     gen_rterm_grad(w + NODE_OFF(n) + NX, up, tv, gr);
     gen_rterm_hess(w + NODE_OFF(n) + NX, up, tv, hr);
-    const double wgt = I.df * DMB_NODE_RW[n];
+    const double wgt = I.df * NODE_RW_OF(n);
 #pragma unroll
     for (int a = 0; a < 2 * NU; ++a) wn[WN_RG + a] = wgt * gr[a];
 #pragma unroll
@@ -473,31 +499,31 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
   // node variables: sum over child edges (+ continuity of the parent edge, terminal cost, rterm)
   for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
     const int n = idx / NVP, i = idx - n * NVP;
-    const int k = DMB_NODE_K[n];
+    const int k = NODE_K_OF(n);
     double go = 0.0, gc = 0.0;
     if (k < NHOR) {
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-        const double* eb = I.eb + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ;
+      for (int j = 0; j < NODE_NEDGE(n); ++j) {
+        const double* eb = I.eb + (size_t)(NODE_FIRST_EDGE(n) + j) * EB_SZ;
         go += eb[EB_GOBJ + i]; gc += eb[EB_GCON + i];
       }
     } else if (i >= NX) { I.gl[idx] = 0.0; if (!I.resto) I.go[idx] = 0.0; continue; }
     if (i < NX) {
-      const int pe = DMB_NODE_PARENT_EDGE[n];
+      const int pe = NODE_PARENT_EDGE(n);
       if (pe >= 0) {
         gc -= I.lam[LAM_EDGE(pe) + NY + i];
         if (k == NHOR) {
           double gm[NX];
           gen_mterm_grad(w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm);
-          go += I.df * DMB_EDGE_OMEGA[pe] * gm[i];
+          go += I.df * EDGE_OMEGA_OF(pe) * gm[i];
         }
       } else gc += I.lam[i];
     } else if (i < NX + NU) {
       const int iu = i - NX;
       go += I.node[(size_t)n * WN_NODE + WN_RG + iu];
       // this node's input is u_prev of every child node that still has a control
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-        const int cn = DMB_EDGE_CHILD[DMB_NODE_FIRST_EDGE[n] + j];
-        if (DMB_NODE_K[cn] == NHOR) continue;
+      for (int j = 0; j < NODE_NEDGE(n); ++j) {
+        const int cn = EDGE_CHILD_OF(NODE_FIRST_EDGE(n) + j);
+        if (NODE_K_OF(cn) == NHOR) continue;
         go += I.node[(size_t)cn * WN_NODE + WN_RG + NU + iu];
       }
     }
@@ -741,6 +767,23 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
 #define DMB_FLAG_OR(flag, bits) (*(flag) |= (bits))
 #endif
 
+#if !defined(DMB_HOSTSIM) && (DMB_NX + 2 * DMB_NU + DMB_NEPS <= 8) && !defined(DMB_NO_DMMA)
+#define DMB_DMMA_SWEEP 1
+// FP64 tensor-core MMA (sm_100a: DMMA.8x8x4): D(8x8) += A(8x4, row) * B(4x8, col).  Fragments per lane (r = lane / 4,
+// q = lane % 4): A[r][q], B[q][r], C/D[r][2q], C/D[r][2q + 1].
+DMB_DEV void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// element (row, col) of a matrix held in the C-fragment layout, delivered to the calling lane (row / col may differ per lane)
+DMB_DEV double frag_get(double c0, double c1, int row, int col) {
+  const int src = row * 4 + (col >> 1);
+  const double v0 = __shfl_sync(DMB_FULL, c0, src), v1 = __shfl_sync(DMB_FULL, c1, src);
+  return (col & 1) ? v1 : v0;
+}
+#else
+#define DMB_DMMA_SWEEP 0
+#endif
+
 // lower-triangle index -> (row i >= column j)
 #define NTRI_VP (NVP * (NVP + 1) / 2)
 #define NTRI_XI (NXI * (NXI + 1) / 2)
@@ -794,7 +837,7 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
   for (int idx = c.tid; idx < NNODE * (NV * NV + NV); idx += c.nthr) {
     const int n = idx / (NV * NV + NV), ent = idx - n * (NV * NV + NV);
     double* wn = I.node + (size_t)n * WN_NODE;
-    const int k = DMB_NODE_K[n];
+    const int k = NODE_K_OF(n);
     const bool is_q = ent >= NV * NV;
     const int a = is_q ? ent - NV * NV : ent / NV, b = is_q ? -1 : ent - (ent / NV) * NV;
     // edge-local index of v-space position a / b (u_prev has none)
@@ -819,8 +862,8 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
     }
     if (k == NHOR) {
       if (a < NX && (is_q || b < NX)) {
-        const int pe = DMB_NODE_PARENT_EDGE[n];
-        const double wgt = I.df * DMB_EDGE_OMEGA[pe];
+        const int pe = NODE_PARENT_EDGE(n);
+        const double wgt = I.df * EDGE_OMEGA_OF(pe);
         if (is_q) { double gm[NX]; gen_mterm_grad(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm); val += wgt * gm[a]; }
         else if (!ls_mode) { double hm[NX * NX]; gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm); val += wgt * hm[a * NX + b]; }
       }
@@ -833,8 +876,8 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         if (ra >= 0 && rb >= 0) val += wn[WN_RH + ra * 2 * NU + rb];
       }
       if (ia >= 0 && (is_q || ib >= 0))
-        for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-          const double* eb = I.er + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * ER_SZ;
+        for (int j = 0; j < NODE_NEDGE(n); ++j) {
+          const double* eb = I.er + (size_t)(NODE_FIRST_EDGE(n) + j) * ER_SZ;
           val += is_q ? eb[ER_GH + ia] + delta * eb[ER_YTY0 + ia] : eb[ER_HH + ia * NVP + ib] + delta * eb[ER_YTY + ia * NVP + ib];
         }
     }
@@ -853,10 +896,134 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
      if (par || c.warp == 0)
      for (int n = DMB_LVL(lvl + 1) - 1 - (par ? c.warp : 0); n >= DMB_LVL(lvl); n -= (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-        const int e = DMB_NODE_FIRST_EDGE[n] + j;
+#if DMB_DMMA_SWEEP
+      if (!LDL) {
+        // ---- tensor-core sweep step (FP64 DMMA), everything in the padded 8 x 8 v-space (x, u_prev, u, eps) -------------------
+        //   F  : child's xi = F v  (rows x_c = [A B] (x,u,eps), rows u_prev_c = u)          T1 = P_c F ,  Q = Q0 + F' T1
+        //   L  = Q_xi,u chol(Q_uu)^-T ,  P = Q_xi,xi - L L'  (one DMMA with k = NUT <= 4) ,  K = -chol^-T L'
+        const int fr = c.lane >> 2, fq = c.lane & 3;
+        double q0 = (fr < NV && 2 * fq < NV) ? wn[WN_Q + fr * NV + 2 * fq] : 0.0;
+        double q1 = (fr < NV && 2 * fq + 1 < NV) ? wn[WN_Q + fr * NV + 2 * fq + 1] : 0.0;
+        double* pbs = Qs + (par ? c.warp : 0) * DMB_QS_WARP;              // NXI : p_c + P_c[:, x] b
+        for (int j = 0; j < NODE_NEDGE(n); ++j) {
+          const int e = NODE_FIRST_EDGE(n) + j;
+          const double* er = I.er + (size_t)e * ER_SZ;
+          const double* wc = I.node + (size_t)EDGE_CHILD_OF(e) * WN_NODE;
+          double fa[2], pa[2];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = kk * 4 + fq, m = fr;                                // F[k][m]
+            const int ia = m < NX ? m : ((m >= NXI && m < NV) ? m - NU : -1);
+            fa[kk] = k < NX ? (ia >= 0 ? er[ER_AB + k * NVP + ia] : 0.0) : ((k < NXI && m == NXI + k - NX) ? 1.0 : 0.0);
+            pa[kk] = (fr < NXI && k < NXI) ? P_AT(wc, fr, k) : 0.0;          // P_c[fr][k]
+          }
+          if (c.lane < NXI) {
+            double sv = wc[WN_QV + c.lane];
+#pragma unroll
+            for (int t = 0; t < NX; ++t) sv += P_AT(wc, c.lane, t) * er[ER_B + t];
+            pbs[c.lane] = sv;
+          }
+          double t0 = 0.0, t1 = 0.0;
+          dmma884(t0, t1, pa[0], fa[0]); dmma884(t0, t1, pa[1], fa[1]);      // T1 = P_c F
+          const double tb0 = frag_get(t0, t1, fq, fr), tb1 = frag_get(t0, t1, 4 + fq, fr);   // B fragments: T1[k][fr]
+          dmma884(q0, q1, fa[0], tb0); dmma884(q0, q1, fa[1], tb1);          // Q += F' T1
+          WARP_SYNC();
+          if (c.lane < NV) {                                                  // q += F' (p_c + P_c b)
+            const int m = c.lane;
+            const int ia = m < NX ? m : (m >= NXI ? m - NU : -1);
+            double sv = (m >= NXI && m < NXI + NU) ? pbs[NX + m - NXI] : 0.0;
+            if (ia >= 0) {
+#pragma unroll
+              for (int k = 0; k < NX; ++k) sv += er[ER_AB + k * NVP + ia] * pbs[k];
+            }
+            wn[WN_QV + m] += sv;
+          }
+          WARP_SYNC();
+        }
+        // complete Q: the control columns / rows stay in shared memory for the re-solves (riccati_vector, forward roll-out)
+        if (fr < NV) {
+          if (2 * fq >= NXI && 2 * fq < NV) wn[WN_Q + fr * NV + 2 * fq] = q0;
+          if (2 * fq + 1 >= NXI && 2 * fq + 1 < NV) wn[WN_Q + fr * NV + 2 * fq + 1] = q1;
+        }
+        // Cholesky of Q_uu, redundantly in every lane (NUT <= 4); diagonal keeps the reciprocal
+        double C[NUT * NUT];
+        int bad = 0;
+#pragma unroll
+        for (int a = 0; a < NUT; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            double sv = frag_get(q0, q1, NXI + a, NXI + b);
+#pragma unroll
+            for (int t = 0; t < b; ++t) sv -= C[a * NUT + t] * C[b * NUT + t];
+            if (a == b) { if (!(sv > 0.0)) { bad = 1; sv = 1.0; } C[a * NUT + a] = rsqrt(sv); }
+            else C[a * NUT + b] = sv * C[b * NUT + b];
+          }
+        if (bad && c.lane == 0) DMB_FLAG_OR(flag, bad);
+        // L[fr][:] = Q[fr][u] chol^-T (forward substitution along the row; all lanes of a row quad compute the same values)
+        double Lr[NUT];
+#pragma unroll
+        for (int a = 0; a < NUT; ++a) {
+          double sv = frag_get(q0, q1, fr, NXI + a);
+#pragma unroll
+          for (int t = 0; t < a; ++t) sv -= Lr[t] * C[a * NUT + t];
+          Lr[a] = sv * C[a * NUT + a];
+        }
+        // vector part: l = chol^-1 q_u ;  k = -chol^-T l ;  p = q_xi - L l
+        WARP_SYNC();
+        double lv[NUT], kv[NUT];
+#pragma unroll
+        for (int a = 0; a < NUT; ++a) {
+          double sv = wn[WN_QV + NXI + a];
+#pragma unroll
+          for (int t = 0; t < a; ++t) sv -= lv[t] * C[a * NUT + t];
+          lv[a] = sv * C[a * NUT + a];
+        }
+#pragma unroll
+        for (int a = NUT - 1; a >= 0; --a) {
+          double sv = lv[a];
+#pragma unroll
+          for (int t = a + 1; t < NUT; ++t) sv -= C[t * NUT + a] * kv[t];
+          kv[a] = sv * C[a * NUT + a];
+        }
+        // gains K[:, fr] = -chol^-T L[fr][:]' (one lane per row quad writes), k
+        if (fq == 0 && fr < NXI) {
+          double z[NUT];
+#pragma unroll
+          for (int a = NUT - 1; a >= 0; --a) {
+            double sv = Lr[a];
+#pragma unroll
+            for (int t = a + 1; t < NUT; ++t) sv -= C[t * NUT + a] * z[t];
+            z[a] = sv * C[a * NUT + a];
+          }
+          double pv = wn[WN_QV + fr];
+#pragma unroll
+          for (int a = 0; a < NUT; ++a) { wn[WN_K + a * NXI + fr] = -z[a]; pv -= Lr[a] * lv[a]; }
+          wn[WN_QV + fr] = pv;
+        }
+        if (c.lane < NUT) wn[WN_KV + c.lane] = -kv[c.lane];
+        // P = Q_xi,xi - L L' : one DMMA (A[fr][fq] = -L[fr][fq], B[fq][fr] = L[fr][fq]); rows / columns beyond xi are not used
+        double la = 0.0;
+#pragma unroll
+        for (int a = 0; a < NUT; ++a) if (fq == a && fr < NXI) la = Lr[a];
+        dmma884(q0, q1, -la, la);
+        // exact symmetry (the recursion amplifies rounding asymmetries on badly scaled problems): mirror the lower triangle
+        {
+          const double m0 = frag_get(q0, q1, 2 * fq, fr), m1 = frag_get(q0, q1, (2 * fq + 1) & 7, fr);
+          if (2 * fq > fr) q0 = m0;
+          if (2 * fq + 1 > fr) q1 = m1;
+        }
+        if (fr < NXI) {
+          if (2 * fq < NXI) wn[WN_Q + fr * NV + 2 * fq] = q0;
+          if (2 * fq + 1 < NXI) wn[WN_Q + fr * NV + 2 * fq + 1] = q1;
+        }
+        WARP_SYNC();
+      } else
+#endif
+      {
+      for (int j = 0; j < NODE_NEDGE(n); ++j) {
+        const int e = NODE_FIRST_EDGE(n) + j;
         const double* er = I.er + (size_t)e * ER_SZ;
-        const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+        const double* wc = I.node + (size_t)EDGE_CHILD_OF(e) * WN_NODE;
         for (int idx = c.lane; idx < NXI * NVP + NXI; idx += DMB_LANES) {
           if (idx < NXI * NVP) {
             const int r = idx / NVP, jj = idx - r * NVP;
@@ -947,6 +1114,7 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
       }
       WARP_SYNC();
      }
+      }
      if (par) CTA_SYNC();            // the next stage reads the cost-to-go of this one
     }
     SUB_TICK(I, 5);
@@ -986,11 +1154,11 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
         dwn[NX + a] = s;
       }
       WARP_SYNC();
-      for (int idx = c.lane; idx < DMB_NODE_NEDGE[n] * NXI; idx += DMB_LANES) {
+      for (int idx = c.lane; idx < NODE_NEDGE(n) * NXI; idx += DMB_LANES) {
         const int j = idx / NXI, r = idx - j * NXI;
-        const int e = DMB_NODE_FIRST_EDGE[n] + j;
+        const int e = NODE_FIRST_EDGE(n) + j;
         const double* er = I.er + (size_t)e * ER_SZ;
-        double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+        double* wc = I.node + (size_t)EDGE_CHILD_OF(e) * WN_NODE;
         double s;
         if (r < NX) {
           s = er[ER_B + r];
@@ -1033,10 +1201,10 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
       // re-solve with a new right-hand side: r_d = Sigma_s rp_d (zero in a refinement solve, where the condensed rows are exact)
       for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? eb[EB_SIGS + i] * res[LAM_EDGE(e) + NY + NX + i] : eb[EB_RD + i]; }
 #endif
-      const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
+      const double* dvp = I.dw + NODE_OFF(EDGE_PARENT_OF(e));
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];
       // continuity multiplier = gradient of the child's cost-to-go
-      const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+      const double* wc = I.node + (size_t)EDGE_CHILD_OF(e) * WN_NODE;
       for (int a = c.gl; a < NX; a += GSZ) {
         double s = wc[WN_QV + a];
 #pragma unroll

@@ -40,7 +40,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
       DMB_COPY_BATCH(DMB_NNZ_J, c.gl, GSZ, eb[EB_JNZ + idx], jz[idx] = dc[DMB_J_ROW[idx]] * val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_GY + idx], T[STG_GY + idx] = val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
-      const double* dvp = I.dw + NODE_OFF(DMB_EDGE_PARENT[e]);
+      const double* dvp = I.dw + NODE_OFF(EDGE_PARENT_OF(e));
       const double* dy = I.dw + EDGE_OFF(e);
       for (int i = c.gl; i < NQ; i += GSZ) dq[i] = i < NVP ? dvp[i] : dy[i - NVP];
       for (int i = c.gl; i < NY + NX; i += GSZ) ln[i] = I.lamn[LAM_EDGE(e) + i];
@@ -86,7 +86,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
         nrm_rhs = fmax(nrm_rhs, fmax(fabs(T[STG_GY + r]), fabs(res[LAM_EDGE(e) + r])));
         nrm_sol = fmax(nrm_sol, fmax(fabs(dq[NVP + r]), fabs(ln[r])));
       }
-      const double* dxc = I.dw + NODE_OFF(DMB_EDGE_CHILD[e]);
+      const double* dxc = I.dw + NODE_OFF(EDGE_CHILD_OF(e));
       for (int a = c.gl; a < NX; a += GSZ) {
         const double rr = res[LAM_EDGE(e) + NY + a] + dq[NVP + DMB_XF_SEL[a]] - dxc[a];
         rp[LAM_EDGE(e) + NY + a] = rr;
@@ -105,7 +105,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
   CTA_SYNC();
   for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
     const int n = idx / NVP, i = idx - n * NVP;
-    const int k = DMB_NODE_K[n];
+    const int k = NODE_K_OF(n);
     if (k == NHOR && i >= NX) { rd[idx] = 0.0; continue; }
     const double* wn = I.node + (size_t)n * WN_NODE;
     const double lo = I.lb[idx], hi = I.ub[idx], wx = I.w[idx], d = I.dw[idx];
@@ -116,29 +116,29 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
     double r = g + sig * d;
     nrm_rhs = fmax(nrm_rhs, fabs(g)); nrm_sol = fmax(nrm_sol, fabs(d));
     if (k < NHOR)
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) r += I.eb[(size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ + EB_GCON + i];
-    const int pe = DMB_NODE_PARENT_EDGE[n];
+      for (int j = 0; j < NODE_NEDGE(n); ++j) r += I.eb[(size_t)(NODE_FIRST_EDGE(n) + j) * EB_SZ + EB_GCON + i];
+    const int pe = NODE_PARENT_EDGE(n);
     if (i < NX) {
       if (pe >= 0) {
         r -= I.lamn[LAM_EDGE(pe) + NY + i];
         if (k == NHOR) {
           double hm[NX * NX];
           gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm);
-          const double wgt = I.df * DMB_EDGE_OMEGA[pe];
+          const double wgt = I.df * EDGE_OMEGA_OF(pe);
           for (int b = 0; b < NX; ++b) r += wgt * hm[i * NX + b] * I.dw[NODE_OFF(n) + b];
         }
       } else r += I.lamn[i];
     } else if (i < NX + NU) {
       const int iu = i - NX;
       // own rterm: rows of u ; children's rterm: rows of their u_prev = this u
-      const double* dup = pe >= 0 ? I.dw + NODE_OFF(DMB_EDGE_PARENT[pe]) + NX : nullptr;
+      const double* dup = pe >= 0 ? I.dw + NODE_OFF(EDGE_PARENT_OF(pe)) + NX : nullptr;
       for (int b = 0; b < NU; ++b) {
         r += wn[WN_RH + iu * 2 * NU + b] * I.dw[NODE_OFF(n) + NX + b];
         if (dup) r += wn[WN_RH + iu * 2 * NU + NU + b] * dup[b];
       }
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-        const int cn = DMB_EDGE_CHILD[DMB_NODE_FIRST_EDGE[n] + j];
-        if (DMB_NODE_K[cn] == NHOR) continue;
+      for (int j = 0; j < NODE_NEDGE(n); ++j) {
+        const int cn = EDGE_CHILD_OF(NODE_FIRST_EDGE(n) + j);
+        if (NODE_K_OF(cn) == NHOR) continue;
         const double* wc = I.node + (size_t)cn * WN_NODE;
         for (int b = 0; b < NU; ++b)
           r += wc[WN_RH + (NU + iu) * 2 * NU + b] * I.dw[NODE_OFF(cn) + NX + b] + wc[WN_RH + (NU + iu) * 2 * NU + NU + b] * I.dw[NODE_OFF(n) + NX + b];
@@ -248,14 +248,14 @@ DMB_PHASE void riccati_vector_t(const Ctx& c, const Inst& I, double delta, doubl
   for (int idx = c.tid; idx < NNODE * NV; idx += c.nthr) {
     const int n = idx / NV, a = idx - n * NV;
     double* wn = I.node + (size_t)n * WN_NODE;
-    const int k = DMB_NODE_K[n];
+    const int k = NODE_K_OF(n);
     const int ia = a < NX ? a : (a >= NXI ? a - NU : -1);
     double val = 0.0;
     if (ia >= 0 && !(k == NHOR && ia >= NX)) {
       val = rd[NODE_OFF(n) + ia];
       if (k < NHOR)
-        for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-          const double* er = I.er + (size_t)(DMB_NODE_FIRST_EDGE[n] + j) * ER_SZ;
+        for (int j = 0; j < NODE_NEDGE(n); ++j) {
+          const double* er = I.er + (size_t)(NODE_FIRST_EDGE(n) + j) * ER_SZ;
           val += er[ER_GH + ia] + delta * er[ER_YTY0 + ia];
         }
     }
@@ -269,10 +269,10 @@ DMB_PHASE void riccati_vector_t(const Ctx& c, const Inst& I, double delta, doubl
      if (par || c.warp == 0)
      for (int n = DMB_LVL(lvl + 1) - 1 - (par ? c.warp : 0); n >= DMB_LVL(lvl); n -= (par ? c.nwarp : 1)) {
       double* wn = I.node + (size_t)n * WN_NODE;
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) {
-        const int e = DMB_NODE_FIRST_EDGE[n] + j;
+      for (int j = 0; j < NODE_NEDGE(n); ++j) {
+        const int e = NODE_FIRST_EDGE(n) + j;
         const double* er = I.er + (size_t)e * ER_SZ;
-        const double* wc = I.node + (size_t)DMB_EDGE_CHILD[e] * WN_NODE;
+        const double* wc = I.node + (size_t)EDGE_CHILD_OF(e) * WN_NODE;
         for (int r = c.lane; r < NXI; r += DMB_LANES) {
           double s = wc[WN_QV + r];
 #pragma unroll

@@ -102,7 +102,7 @@ DMB_DEV void sens_rhs(const Ctx& c, const Inst& I, int pj) {
     if (pj >= DMB_P_TVP && pj < DMB_P_TVP + (NHOR + 1) * DMB_NTVP) { k_sel = (pj - DMB_P_TVP) / (DMB_NTVP > 0 ? DMB_NTVP : 1); jth = (pj - DMB_P_TVP) - k_sel * DMB_NTVP; }
     else { c_sel = (pj - DMB_P_P) / (DMB_NPM > 0 ? DMB_NPM : 1); jth = DMB_NTVP + (pj - DMB_P_P) - c_sel * DMB_NPM; }
     for (int e = c.tid; e < NEDGE; e += c.nthr) {
-      if (k_sel >= 0 ? DMB_EDGE_K[e] != k_sel : DMB_EDGE_PIDX[e] != c_sel) continue;
+      if (k_sel >= 0 ? EDGE_K_OF(e) != k_sel : EDGE_PIDX_OF(e) != c_sel) continue;
       double q[NQ], lg[NY > 0 ? NY : 1], ln[NNL > 0 ? NNL : 1], dq[NQ], dG[NY > 0 ? NY : 1], dD[NNL > 0 ? NNL : 1];
       gather_q(I.w, e, q);
       const double* le = I.lam + LAM_EDGE(e);
@@ -116,7 +116,7 @@ DMB_DEV void sens_rhs(const Ctx& c, const Inst& I, int pj) {
       for (int i = 0; i < NY; ++i) dG[i] = 0.0;
 #pragma unroll
       for (int i = 0; i < NNL; ++i) dD[i] = 0.0;
-      gen_dtheta(jth, q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, DMB_EDGE_OMEGA[e], 1.0, ln, dq, dG, dD);
+      gen_dtheta(jth, q, edge_tvp(I.p, e), edge_pp(I.p, e), lg, EDGE_OMEGA_OF(e), 1.0, ln, dq, dG, dD);
       double* eb = I.eb + (size_t)e * EB_SZ;
 #if NNL > 0
       // active inequality rows: condensed  J_d' Sigma_s (J_d dq + dd/dtheta)
@@ -134,34 +134,34 @@ DMB_DEV void sens_rhs(const Ctx& c, const Inst& I, int pj) {
     CTA_SYNC();
     for (int idx = c.tid; idx < NNODE * NVP; idx += c.nthr) {
       const int n = idx / NVP, i = idx - n * NVP;
-      if (DMB_NODE_K[n] == NHOR) continue;
+      if (NODE_K_OF(n) == NHOR) continue;
       double s = 0.0;
-      for (int j = 0; j < DMB_NODE_NEDGE[n]; ++j) s += I.eb[(size_t)(DMB_NODE_FIRST_EDGE[n] + j) * EB_SZ + EB_GCON + i];
+      for (int j = 0; j < NODE_NEDGE(n); ++j) s += I.eb[(size_t)(NODE_FIRST_EDGE(n) + j) * EB_SZ + EB_GCON + i];
       I.go[idx] = s;
     }
     CTA_SYNC();
     // terminal cost (leaf nodes) and input penalty (time-varying weights) — rare, cheap: thread per node / one thread
     for (int n = c.tid; n < NNODE; n += c.nthr) {
-      if (DMB_NODE_K[n] != NHOR) continue;
-      const int pe = DMB_NODE_PARENT_EDGE[n];
-      if (k_sel >= 0 ? k_sel != NHOR : DMB_EDGE_PIDX[pe] != c_sel) continue;
+      if (NODE_K_OF(n) != NHOR) continue;
+      const int pe = NODE_PARENT_EDGE(n);
+      if (k_sel >= 0 ? k_sel != NHOR : EDGE_PIDX_OF(pe) != c_sel) continue;
       double o[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) o[i] = 0.0;
       gen_mterm_dtheta(jth, I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), o);
-      for (int i = 0; i < NX; ++i) I.go[NODE_OFF(n) + i] += DMB_EDGE_OMEGA[pe] * o[i];
+      for (int i = 0; i < NX; ++i) I.go[NODE_OFF(n) + i] += EDGE_OMEGA_OF(pe) * o[i];
     }
 #if DMB_NTVP > 0
     if (k_sel >= 0 && k_sel < NHOR && c.tid == 0) {
       for (int n = 0; n < NNODE; ++n) {
-        if (DMB_NODE_K[n] != k_sel) continue;
+        if (NODE_K_OF(n) != k_sel) continue;
         double up[NU], o[2 * NU];
         for (int a = 0; a < NU; ++a) { up[a] = node_uprev(I, I.w, n, a); o[a] = 0.0; o[NU + a] = 0.0; }
         gen_rterm_dtvp(jth, I.w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + k_sel * DMB_NTVP, o);
-        const int pe = DMB_NODE_PARENT_EDGE[n];
+        const int pe = NODE_PARENT_EDGE(n);
         for (int a = 0; a < NU; ++a) {
-          I.go[NODE_OFF(n) + NX + a] += DMB_NODE_RW[n] * o[a];
-          if (pe >= 0) I.go[NODE_OFF(DMB_EDGE_PARENT[pe]) + NX + a] += DMB_NODE_RW[n] * o[NU + a];
+          I.go[NODE_OFF(n) + NX + a] += NODE_RW_OF(n) * o[a];
+          if (pe >= 0) I.go[NODE_OFF(EDGE_PARENT_OF(pe)) + NX + a] += NODE_RW_OF(n) * o[NU + a];
         }
       }
     }

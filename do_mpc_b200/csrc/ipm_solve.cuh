@@ -649,7 +649,7 @@ DMB_DEV void load_initial_guess(const Ctx& c, const double* x_flat, const double
       else if (i >= NNODE * NVP) {
         // auxiliary end-of-interval state of a discrete edge: start from the child's node state
         const int e = (i - NNODE * NVP) / NY, j = (i - NNODE * NVP) % NY;
-        v = x_flat[DMB_NODE_X_FLAT[DMB_EDGE_CHILD[e]] + (j - DMB_NZ)];
+        v = x_flat[DMB_NODE_X_FLAT[EDGE_CHILD_OF(e)] + (j - DMB_NZ)];
       }
     } else {
       if (i < NNODE * NVP) {
