@@ -72,21 +72,73 @@ def _cpu_worker(args):
     return r["success"], r["iter_count"], time.perf_counter() - t
 
 
+def effective_cores():
+    """cores this process may really use: min(os.cpu_count(), scheduler affinity, cgroup CPU quota).  The GPU boxes of this
+    pool report 128 logical CPUs but run inside a cgroup with a much smaller quota (shared host): 128 worker processes on such
+    a box only time-slice (round 1 measured 28 and 148 solves/s on two 'identical 128-core' boxes for that reason)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 class CpuPool:
-    """All host cores, one oracle solver per worker process, one BLAS thread each (the reference's own idiom for parallel
-    sampling: examples/tools/sampling/multiprocessing/closed_loop/mp_sampling_closed_loop_02.py:21-24,69-70)."""
+    """Host cores, one oracle solver per worker process, one BLAS thread each (the reference's own idiom for parallel sampling:
+    examples/tools/sampling/multiprocessing/closed_loop/mp_sampling_closed_loop_02.py:21-24,69-70).  The NLP is built once in
+    the parent (workers inherit it through fork).  The worker count is calibrated: starting from the cores the OS reports it is
+    halved while the throughput does not drop — on a shared host with a CPU quota more processes than real cores only
+    time-slice, and `cores` must say what was really used."""
 
     def __init__(self, x0, up):
         import multiprocessing as mp
-        self.cores = os.cpu_count() or 1
+        from oracle import models
+        from oracle.ipm import IPMSolver, IpmOptions
+        from oracle.nlp import FlatNLP
+        _W["nlp"] = FlatNLP(models.cstr_nominal())
+        _W["sol"] = IPMSolver(_W["nlp"], IpmOptions(max_iter=300))
+        self.mp = mp.get_context("fork")
+        self.logical_cpus = os.cpu_count() or 1
         self.x0, self.up = x0, up
-        self.pool = mp.get_context("fork").Pool(self.cores)
-        # build the NLP per worker (untimed), then calibrate the rate on two instances per core
-        self.pool.map(_cpu_worker, [(x0[i % len(x0)], up[i % len(x0)]) for i in range(self.cores)], chunksize=1)
-        self.rate, _, _, _ = self.run(2 * self.cores)
+        self.pool = None
+        n = effective_cores()
+        best = None
+        self.calibration = []
+        while n >= 1:
+            self._open(n)
+            rate, dt, _, ts = self.run(3 * n)
+            self.calibration.append({"procs": n, "solves_per_s": round(rate, 2), "ms_per_solve": round(1e3 * ts, 1)})
+            if best is not None and rate < 0.93 * best[1]:
+                break
+            if best is None or rate >= 0.93 * best[1]:
+                best = (n, max(rate, best[1]) if best else rate)
+            n //= 2
+        self._open(best[0])
+        self.cores = best[0]
+        self.rate = best[1]
+
+    def _open(self, n):
+        if self.pool is not None:
+            self.pool.close(); self.pool.join()
+        self.pool = self.mp.Pool(n)
+        self.nproc = n
+        k = len(self.x0)
+        self.pool.map(_cpu_worker, [(self.x0[i % k], self.up[i % k]) for i in range(n)], chunksize=1)     # untimed warm-up of every worker
 
     def sample_size(self, B, seconds):
-        """the whole batch when it fits into `seconds` of wall time, else a bounded sample (multiple of the core count)"""
+        """the whole batch when it fits into `seconds` of wall time, else a bounded sample (multiple of the worker count)"""
         n = int(self.rate * seconds)
         return B if n >= B else max(self.cores, (n // self.cores) * self.cores)
 
@@ -98,14 +150,14 @@ class CpuPool:
         return n_sample / dt, dt, float(np.mean([r[0] for r in res])), float(np.mean([r[2] for r in res]))
 
     def close(self):
-        self.pool.close()
+        self.pool.close(); self.pool.join()
 
 
 def cpu_baseline_record(cp, v, dt, succ, t_solve, n_sample, B):
-    return {"value": v, "unit": UNIT, "cores": cp.cores, "kind": "port", "per_core": v / cp.cores,
-            "ms_per_solve_one_core": 1e3 * t_solve, "same_config": bool(n_sample == B),
+    return {"value": v, "unit": UNIT, "cores": cp.cores, "logical_cpus": cp.logical_cpus, "kind": "port", "per_core": v / cp.cores,
+            "ms_per_solve_one_core": 1e3 * t_solve, "same_config": bool(n_sample == B), "calibration": cp.calibration,
             "sample": f"{n_sample} of the {B} instances of the same batch per step ({dt:.1f} s), oracle/ipm.py (numpy restatement of IPOPT, "
-                      f"block LDL^T with exact inertia) on {cp.cores} processes x 1 BLAS thread; success rate {succ:.3f}; {IPOPT_NOTE}"}
+                      f"block LDL^T with exact inertia) on {cp.cores} processes x 1 BLAS thread (calibrated: more processes did not raise the throughput; the OS reports {cp.logical_cpus} logical CPUs); success rate {succ:.3f}; {IPOPT_NOTE}"}
 
 
 def clocks_sampler(stop, out):
@@ -315,6 +367,9 @@ def main():
         for _ in range(args.warmup):
             step_fn()
         barrier()
+        if not th.is_alive() and not stop.is_set():
+            th.start()                                     # clocks are sampled from the end of the first warm-up on (no fork()
+                                                           # of the nvidia-smi child while the first launch loads the module)
         evs, kms = [], []
         for _ in range(args.steps):
             flush.zero_()                                  # L2 flush between timed iterations (outside the timed events)
@@ -330,7 +385,7 @@ def main():
         return float(tot.item()) / args.steps, kms
 
     stop = threading.Event(); samples = []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True); th.start()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True)
 
     # ---- weak scaling (headline): every rank solves `B` instances ---------------------------------------------------------------
     out = None

@@ -2,6 +2,8 @@
 // Compiled once per generated problem (problem_gen.h on the include path) for sm_100a.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <new>
 
@@ -204,6 +206,7 @@ struct dmb_solver {
   double* d_stage = nullptr; size_t stage_doubles = 0;
   double* h_stage = nullptr; size_t h_stage_doubles = 0;
   int last_grid = 0; long long n_launches = 0; float last_ms = 0.f;
+  size_t l2_window_bytes = 0; float l2_hit_ratio = 1.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
 };
@@ -245,6 +248,18 @@ dmb_solver* dmb_create(int device) {
             cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
   if (!ok) { dmb_destroy(s); return nullptr; }
   s->ws_slots = s->grid_max;
+  {
+    // L2 persistence window over the workspace slots (DMB_L2_PERSIST=0 switches it off)
+    const char* env = getenv("DMB_L2_PERSIST");
+    const size_t ws_bytes = sizeof(double) * (size_t)SLOT_DOUBLES * s->grid_max;
+    if (!(env && env[0] == '0') && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      const size_t carve = ws_bytes < (size_t)prop.persistingL2CacheMaxSize ? ws_bytes : (size_t)prop.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        s->l2_window_bytes = ws_bytes < (size_t)prop.accessPolicyMaxWindowSize ? ws_bytes : (size_t)prop.accessPolicyMaxWindowSize;
+        s->l2_hit_ratio = ws_bytes <= carve ? 1.f : (float)((double)carve / (double)ws_bytes);
+      } else (void)cudaGetLastError();
+    }
+  }
   return s;
 }
 
@@ -306,7 +321,22 @@ int dmb_solve_device_ws(dmb_solver* s, int B, const double* d_x_init, const doub
     s->n_launches++;
   }
   CK(cudaEventRecord(s->ev0, st));
-  dmb_solve_kernel<<<grid, DMB_THREADS, SM_BYTES, st>>>(a);
+  if (s->l2_window_bytes > 0) {
+    // the per-CTA workspace slots (L2-resident scratch, rewritten every IPM iteration) are marked persisting for this launch so
+    // that the L2 keeps the dirty lines instead of writing them back to DRAM between iterations (profiles/README.md: traffic)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DMB_THREADS); cfg.dynamicSmemBytes = SM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = s->d_ws;
+    at[0].val.accessPolicyWindow.num_bytes = s->l2_window_bytes;
+    at[0].val.accessPolicyWindow.hitRatio = s->l2_hit_ratio;
+    at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, dmb_solve_kernel, a));
+  } else
+    dmb_solve_kernel<<<grid, DMB_THREADS, SM_BYTES, st>>>(a);
   CK(cudaEventRecord(s->ev1, st));
   CK(cudaGetLastError());
   s->last_grid = grid; s->n_launches++;
@@ -342,39 +372,42 @@ int dmb_solve_host_ws(dmb_solver* s, int B, const double* x_init, const double* 
   if (B <= 0 || !p || !f || !status || !iters || !u0) { s->err = "invalid argument"; return DMB_E_ARG; }
   CK(cudaSetDevice(s->device));
   const size_t nB = (size_t)B;
-  // device layout of the staging buffer (doubles)
+  const bool have_z = z0s && DMB_NZ > 0;
+  // one staging image, identical on the host (pinned) and on the device: inputs first, outputs behind them, so that a call
+  // costs ONE host->device and ONE device->host transfer from / to page-locked memory
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 1) & ~(size_t)1; return o; };
-  const size_t o_p = take(nB * DMB_NP), o_xi = take(x_init ? nB * DMB_NW : 0), o_x0 = take(x0s ? nB * NX : 0),
-               o_u0s = take(u0s ? nB * NU : 0), o_z0 = take(z0s ? nB * DMB_NZ : 0), o_x = take(x ? nB * DMB_NW : 0),
-               o_lg = take(lam_g ? nB * DMB_NG : 0), o_lx = take(lam_x ? nB * DMB_NW : 0), o_g = take(g ? nB * DMB_NG : 0),
-               o_f = take(nB), o_u = take(nB * NU), o_st = take(stats ? nB * DMB_NSTAT : 0), o_i1 = take(nB), o_i2 = take(nB),
-               o_lg0 = take(lam_g0 ? nB * DMB_NG : 0), o_lx0 = take(lam_x0 ? nB * DMB_NW : 0);
+  const size_t o_p = take(nB * DMB_NP), o_xi = take(x_init ? nB * DMB_NW : 0), o_lg0 = take(lam_g0 ? nB * DMB_NG : 0),
+               o_lx0 = take(lam_x0 ? nB * DMB_NW : 0), o_x0 = take(x0s ? nB * NX : 0), o_u0s = take(u0s ? nB * NU : 0),
+               o_z0 = take(have_z ? nB * DMB_NZ : 0);
+  const size_t n_in = off;
+  const size_t o_x = take(x ? nB * DMB_NW : 0), o_lg = take(lam_g ? nB * DMB_NG : 0), o_lx = take(lam_x ? nB * DMB_NW : 0),
+               o_g = take(g ? nB * DMB_NG : 0), o_f = take(nB), o_u = take(nB * NU), o_st = take(stats ? nB * DMB_NSTAT : 0),
+               o_i1 = take(nB), o_i2 = take(nB);
   int rc = ensure_stage(s, off);
   if (rc) return rc;
-  double* d = s->d_stage;
-  CK(cudaMemcpyAsync(d + o_p, p, nB * DMB_NP * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (x_init) CK(cudaMemcpyAsync(d + o_xi, x_init, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (lam_g0) CK(cudaMemcpyAsync(d + o_lg0, lam_g0, nB * DMB_NG * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (lam_x0) CK(cudaMemcpyAsync(d + o_lx0, lam_x0, nB * DMB_NW * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (x0s) CK(cudaMemcpyAsync(d + o_x0, x0s, nB * NX * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (u0s) CK(cudaMemcpyAsync(d + o_u0s, u0s, nB * NU * sizeof(double), cudaMemcpyHostToDevice, 0));
-  if (z0s && DMB_NZ > 0) CK(cudaMemcpyAsync(d + o_z0, z0s, nB * DMB_NZ * sizeof(double), cudaMemcpyHostToDevice, 0));
+  if (off > s->h_stage_doubles) {
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    s->h_stage = nullptr; s->h_stage_doubles = 0;
+    CK(cudaMallocHost(&s->h_stage, off * sizeof(double)));
+    s->h_stage_doubles = off;
+  }
+  double* d = s->d_stage; double* h = s->h_stage;
+  auto put = [&](size_t o, const double* src, size_t n) { if (src && n) memcpy(h + o, src, n * sizeof(double)); };
+  put(o_p, p, nB * DMB_NP); put(o_xi, x_init, nB * DMB_NW); put(o_lg0, lam_g0, nB * DMB_NG); put(o_lx0, lam_x0, nB * DMB_NW);
+  put(o_x0, x0s, nB * NX); put(o_u0s, u0s, nB * NU); if (have_z) put(o_z0, z0s, nB * DMB_NZ);
+  CK(cudaMemcpyAsync(d, h, n_in * sizeof(double), cudaMemcpyHostToDevice, 0));
   rc = dmb_solve_device_ws(s, B, x_init ? d + o_xi : nullptr, lam_g0 ? d + o_lg0 : nullptr, lam_x0 ? d + o_lx0 : nullptr, x0s ? d + o_x0 : nullptr, u0s ? d + o_u0s : nullptr,
-                        (z0s && DMB_NZ > 0) ? d + o_z0 : nullptr, d + o_p, x ? d + o_x : nullptr, lam_g ? d + o_lg : nullptr,
+                        have_z ? d + o_z0 : nullptr, d + o_p, x ? d + o_x : nullptr, lam_g ? d + o_lg : nullptr,
                         lam_x ? d + o_lx : nullptr, g ? d + o_g : nullptr, d + o_f, (int*)(d + o_i1), (int*)(d + o_i2),
                         d + o_u, stats ? d + o_st : nullptr, nullptr);
   if (rc) return rc;
-  if (x) CK(cudaMemcpyAsync(x, d + o_x, nB * DMB_NW * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  if (lam_g) CK(cudaMemcpyAsync(lam_g, d + o_lg, nB * DMB_NG * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  if (lam_x) CK(cudaMemcpyAsync(lam_x, d + o_lx, nB * DMB_NW * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  if (g) CK(cudaMemcpyAsync(g, d + o_g, nB * DMB_NG * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  if (stats) CK(cudaMemcpyAsync(stats, d + o_st, nB * DMB_NSTAT * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(f, d + o_f, nB * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(u0, d + o_u, nB * NU * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(status, d + o_i1, nB * sizeof(int), cudaMemcpyDeviceToHost, 0));
-  CK(cudaMemcpyAsync(iters, d + o_i2, nB * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(h + n_in, d + n_in, (off - n_in) * sizeof(double), cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
+  auto get = [&](double* dst, size_t o, size_t n) { if (dst && n) memcpy(dst, h + o, n * sizeof(double)); };
+  get(x, o_x, nB * DMB_NW); get(lam_g, o_lg, nB * DMB_NG); get(lam_x, o_lx, nB * DMB_NW); get(g, o_g, nB * DMB_NG);
+  get(f, o_f, nB); get(u0, o_u, nB * NU); get(stats, o_st, nB * DMB_NSTAT);
+  memcpy(status, h + o_i1, nB * sizeof(int)); memcpy(iters, h + o_i2, nB * sizeof(int));
   cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
   return DMB_E_OK;
 }
@@ -466,7 +499,12 @@ int dmb_get_stats(dmb_solver* s, int* grid, int* block, int* smem_bytes, long lo
   if (block) *block = DMB_THREADS;
   if (smem_bytes) *smem_bytes = (int)SM_BYTES;
   if (n_launches) *n_launches = s->n_launches;
-  if (last_kernel_ms) { cudaEventSynchronize(s->ev1); cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1); *last_kernel_ms = s->last_ms; }
+  if (last_kernel_ms) {
+    // events that were never recorded make cudaEventElapsedTime fail with cudaErrorInvalidResourceHandle and that error would be
+    // picked up by the cudaGetLastError() check of the NEXT launch: only query after a launch, and never leave an error behind
+    if (s->n_launches > 0 && cudaEventSynchronize(s->ev1) == cudaSuccess && cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1) == cudaSuccess) *last_kernel_ms = s->last_ms;
+    else { (void)cudaGetLastError(); *last_kernel_ms = 0.f; }
+  }
   return DMB_E_OK;
 }
 

@@ -834,17 +834,23 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
   CTA_SYNC();                       // every thread has consumed the flag of a previous call before it is reset
   if (c.tid == 0) *flag = 0;
   // ---- (1) node matrices ------------------------------------------------------------------------------------------
-  for (int idx = c.tid; idx < NNODE * (NV * NV + NV); idx += c.nthr) {
-    const int n = idx / (NV * NV + NV), ent = idx - n * (NV * NV + NV);
+  // Two kinds of work items, so that the bound terms (five dependent-free global loads, a division each) are evaluated ONCE
+  // per variable instead of once for the diagonal and once for the gradient entry:
+  //   items [0, NNODE * NV)            : v-position a of node n -> diagonal entry Q[a][a] and gradient entry q[a]
+  //   items [NNODE * NV, ... + NV*NV)  : off-diagonal entries
+  for (int idx = c.tid; idx < NNODE * (NV + NV * NV); idx += c.nthr) {
+    const bool diag = idx < NNODE * NV;
+    const int rem = diag ? idx : idx - NNODE * NV;
+    const int n = diag ? rem / NV : rem / (NV * NV);
+    const int a = diag ? rem - n * NV : (rem - n * NV * NV) / NV;
+    const int b = diag ? a : (rem - n * NV * NV) - a * NV;
+    if (!diag && a == b) continue;
     double* wn = I.node + (size_t)n * WN_NODE;
     const int k = NODE_K_OF(n);
-    const bool is_q = ent >= NV * NV;
-    const int a = is_q ? ent - NV * NV : ent / NV, b = is_q ? -1 : ent - (ent / NV) * NV;
     // edge-local index of v-space position a / b (u_prev has none)
-    const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < 0 ? -1 : (b < NX ? b : (b >= NXI ? b - NU : -1));
-    double val = 0.0;
-    const bool exists = ia >= 0 && !(k == NHOR && ia >= NX);
-    if (exists && (is_q || a == b)) {
+    const int ia = a < NX ? a : (a >= NXI ? a - NU : -1), ib = b < NX ? b : (b >= NXI ? b - NU : -1);
+    double val = 0.0, gq = 0.0;                                  // matrix entry (a, b); gradient entry a (diag items only)
+    if (diag && ia >= 0 && !(k == NHOR && ia >= NX)) {
       const int gi = NODE_OFF(n) + ia;
       const double lo = I.lb[gi], hi = I.ub[gi], wx = I.w[gi];
       const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
@@ -858,30 +864,32 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         if (hl) { const double sl = wx - lo; sig += I.zL[gi] / sl; gb -= mu / sl; if (!hu) gb += kappa_d * mu; }
         if (hu) { const double su = hi - wx; sig += I.zU[gi] / su; gb += mu / su; if (!hl) gb -= kappa_d * mu; }
       }
-      val = is_q ? gb : sig;
+      val = sig; gq = gb;
     }
     if (k == NHOR) {
-      if (a < NX && (is_q || b < NX)) {
+      if (a < NX && b < NX) {
         const int pe = NODE_PARENT_EDGE(n);
         const double wgt = I.df * EDGE_OMEGA_OF(pe);
-        if (is_q) { double gm[NX]; gen_mterm_grad(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm); val += wgt * gm[a]; }
-        else if (!ls_mode) { double hm[NX * NX]; gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm); val += wgt * hm[a * NX + b]; }
+        if (diag) { double gm[NX]; gen_mterm_grad(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm); gq += wgt * gm[a]; }
+        if (!ls_mode) { double hm[NX * NX]; gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm); val += wgt * hm[a * NX + b]; }
       }
     } else {
       // rterm couples u (v-pos NXI..) and u_prev (v-pos NX..)
       const int ra = (a >= NXI && a < NXI + NU) ? a - NXI : ((a >= NX && a < NXI) ? NU + a - NX : -1);
-      if (is_q) { if (ra >= 0) val += wn[WN_RG + ra]; }
-      else if (!ls_mode) {
+      if (diag && ra >= 0) gq += wn[WN_RG + ra];
+      if (!ls_mode) {
         const int rb = (b >= NXI && b < NXI + NU) ? b - NXI : ((b >= NX && b < NXI) ? NU + b - NX : -1);
         if (ra >= 0 && rb >= 0) val += wn[WN_RH + ra * 2 * NU + rb];
       }
-      if (ia >= 0 && (is_q || ib >= 0))
+      if (ia >= 0)
         for (int j = 0; j < NODE_NEDGE(n); ++j) {
           const double* eb = I.er + (size_t)(NODE_FIRST_EDGE(n) + j) * ER_SZ;
-          val += is_q ? eb[ER_GH + ia] + delta * eb[ER_YTY0 + ia] : eb[ER_HH + ia * NVP + ib] + delta * eb[ER_YTY + ia * NVP + ib];
+          if (diag) gq += eb[ER_GH + ia] + delta * eb[ER_YTY0 + ia];
+          if (ib >= 0) val += eb[ER_HH + ia * NVP + ib] + delta * eb[ER_YTY + ia * NVP + ib];
         }
     }
-    wn[WN_Q + ent] = val;
+    wn[WN_Q + a * NV + b] = val;
+    if (diag) wn[WN_QV + a] = gq;
   }
   CTA_SYNC();
   SUB_START();
@@ -1135,6 +1143,46 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
   SUB_START();
   const bool par = DMB_TREE_PAR && c.nwarp > 1;     // scenario trees: the nodes of a stage roll out on different warps
   {
+#if DMB_NSCEN == 1 && !defined(DMB_HOSTSIM) && (NXI <= 8) && (NVP <= 8) && !defined(DMB_NO_CHAIN_ROLLOUT)
+    // chains: the state step d xi travels in registers (lane t owns d xi_t), broadcast by shuffles; nothing on the dependent
+    // chain goes through memory (the iterate vectors live in the L2-backed slot for cfg #2: the former roll-out paid a global
+    // store -> load round trip per node, ~1.2k cycles; r2 profile gpurun_out/r2d_r1_prof.json: fwd_sweep 7.6 % of the cycles)
+    if (c.warp == 0) {
+      const int t = c.lane;
+      double dxi = t < NX ? -res[t] : 0.0;
+      for (int n = 0; n <= NHOR; ++n) {
+        double* wn = I.node + (size_t)n * WN_NODE;
+        double* dwn = I.dw + NODE_OFF(n);
+        if (t < NXI) wn[WN_DXI + t] = dxi;                 // kept for the multiplier recovery below
+        if (n == NHOR) { if (t < NVP) dwn[t] = t < NX ? dxi : 0.0; break; }
+        double xv[NXI], du[NUT];
+#pragma unroll
+        for (int i = 0; i < NXI; ++i) xv[i] = __shfl_sync(DMB_FULL, dxi, i);
+#pragma unroll
+        for (int a = 0; a < NUT; ++a) {
+          double sv = wn[WN_KV + a];
+#pragma unroll
+          for (int i = 0; i < NXI; ++i) sv += wn[WN_K + a * NXI + i] * xv[i];
+          du[a] = sv;
+        }
+        double dus = 0.0;                                   // du[t - NX] of this lane
+#pragma unroll
+        for (int a = 0; a < NUT; ++a) if (t - NX == a) dus = du[a];
+        if (t < NVP) dwn[t] = t < NX ? dxi : dus;
+        const double* er = I.er + (size_t)n * ER_SZ;
+        double sv = 0.0;
+        if (t < NX) {
+          sv = er[ER_B + t];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) sv += er[ER_AB + t * NVP + i] * xv[i];
+#pragma unroll
+          for (int a = 0; a < NUT; ++a) sv += er[ER_AB + t * NVP + NX + a] * du[a];
+        } else if (t < NXI) sv = dus;
+        dxi = sv;
+      }
+      WARP_SYNC();
+    }
+#else
     for (int lvl = 0; lvl <= NHOR; ++lvl) {
      if (par || c.warp == 0)
      for (int n = DMB_LVL(lvl) + (par ? c.warp : 0); n < DMB_LVL(lvl + 1); n += (par ? c.nwarp : 1)) {
@@ -1171,6 +1219,7 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
      }
      if (par) CTA_SYNC();              // the next stage starts from the states written here
     }
+#endif
     if (c.warp == 0) {
       const double* w0 = I.node;
       for (int a = c.lane; a < NX; a += DMB_LANES) {
