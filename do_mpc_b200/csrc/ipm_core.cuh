@@ -331,6 +331,28 @@ DMB_DEV int group_argmax(const Ctx& c, double val, int idx) {
 }
 #endif
 
+#if !defined(DMB_HOSTSIM) && !defined(DMB_NO_DMMA)
+// FP64 tensor-core MMA (sm_100a: DMMA.8x8x4): D(8x8) += A(8x4, row) * B(4x8, col).  Fragments per lane (r = lane / 4,
+// q = lane % 4): A[r][q], B[q][r], C/D[r][2q], C/D[r][2q + 1].
+DMB_DEV void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// element (row, col) of a matrix held in the C-fragment layout, delivered to the calling lane (row / col may differ per lane)
+DMB_DEV double frag_get(double c0, double c1, int row, int col) {
+  const int src = row * 4 + (col >> 1);
+  const double v0 = __shfl_sync(DMB_FULL, c0, src), v1 = __shfl_sync(DMB_FULL, c1, src);
+  return (col & 1) ? v1 : v0;
+}
+// projection products of the factor phase: only with one tile per warp (NY > 16).  Measured on B200 (round 2, r2l): with two
+// 16-lane groups per warp the tiles take turns on the tensor pipe and the dense H_d build costs more than the products save
+// (cfg #2, NY = 12: 27.65 ms with / 27.24 ms without); NY = 24 / 36 / 30 (cfg #3 / #4 / #5): +2 % / +3 % / +5.5 % throughput
+#define DMB_DMMA_FACTOR (DMB_NY > 16)
+#define DMB_DMMA_SWEEP (DMB_NX + 2 * DMB_NU + DMB_NEPS <= 8)  // Riccati sweep in the 8 x 8 padded v-space
+#else
+#define DMB_DMMA_FACTOR 0
+#define DMB_DMMA_SWEEP 0
+#endif
+
 // batched copy: all loads of a lane are issued before the first store (the two pointers may alias for the
 // compiler, which otherwise serialises load -> store -> load through the memory latency)
 #ifdef DMB_NO_COPY_BATCH
@@ -669,6 +691,99 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     SUB_TICK(I, 2);
     if (act) {
       for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; eb[EB_Y + idx] = T[r * TILE_LD + NY + idx - r * NE]; }
+#if DMB_DMMA_FACTOR
+    }
+    // ---- projection products on the FP64 tensor cores (DMMA.8x8x4) ---------------------------------------------------------
+    // dense H_d = H_yy + Sigma_y in the LU area of the tile (the factors are already saved to the slot), N = H_vy Yext stays
+    // sparse / scalar; then all 32 lanes of the warp work on one tile at a time:
+    //   M = H_d Yext (+ g_y in the right-hand-side column),   Y'M  and  Y'Yext  -> reduced Hessian / gradient blocks
+    if (act) for (int i = c.gl; i < NY * NY; i += GSZ) T[(i / NY) * TILE_LD + i % NY] = 0.0;
+    WARP_SYNC();
+    if (act) {
+      for (int k = c.gl; k < DMB_NNZ_H; k += GSZ) {
+        const int r = DMB_H_ROW[k], cq = DMB_H_COL[k];
+        if (r >= NVP && cq >= NVP) { const double v = T[STG_HNZ + k]; T[(r - NVP) * TILE_LD + cq - NVP] = v; T[(cq - NVP) * TILE_LD + r - NVP] = v; }
+      }
+      for (int idx = c.gl; idx < NVP * NE; idx += GSZ) {
+        const int rq = idx / NE, a = idx - rq * NE;
+        double s = 0.0;
+        for (int t = DMB_HR_START[rq]; t < DMB_HR_START[rq + 1]; ++t) {
+          const int cq = DMB_HR_COL[t];
+          if (cq >= NVP) s += T[STG_HNZ + DMB_HR_IDX[t]] * T[(cq - NVP) * TILE_LD + NY + a];
+        }
+        T[STG_N + rq * NE + a] = s;
+      }
+    }
+    WARP_SYNC();
+    if (act) for (int i = c.gl; i < NY; i += GSZ) T[i * TILE_LD + i] += T[STG_SIGY + i];
+    WARP_SYNC();
+    SUB_TICK(I, 3);
+    {
+      constexpr int GPW = 32 / GSZ;                               // lane groups (= tiles) per warp
+      const int fr = c.lane >> 2, fq = c.lane & 3;
+#pragma unroll 1
+      for (int g = 0; g < GPW; ++g) {
+        const int gid = (c.grp / GPW) * GPW + g;
+        const int eg = e0 + gid;
+        if (eg >= NEDGE) continue;                                // uniform over the warp
+        double* Tg = tile_base + (size_t)gid * TILE_SZ;
+        double* erg = I.er + (size_t)eg * ER_SZ;
+        // M = H_d Yext
+#pragma unroll 1
+        for (int mt = 0; mt < (NY + 7) / 8; ++mt)
+#pragma unroll 1
+          for (int nt = 0; nt < (NE + 7) / 8; ++nt) {
+            double c0 = 0.0, c1 = 0.0;
+            const int row = mt * 8 + fr, col = nt * 8 + fr;
+#pragma unroll
+            for (int kk = 0; kk < (NY + 3) / 4; ++kk) {
+              const int k = kk * 4 + fq;
+              const double av = (row < NY && k < NY) ? Tg[row * TILE_LD + k] : 0.0;
+              const double bv = (k < NY && col < NE) ? Tg[k * TILE_LD + NY + col] : 0.0;
+              dmma884(c0, c1, av, bv);
+            }
+            const int oc = nt * 8 + 2 * fq;
+            if (row < NY) {
+              if (oc < NE) Tg[row * TILE_LD + TILE_M + oc] = c0 + (oc == NVP ? Tg[STG_GY + row] : 0.0);
+              if (oc + 1 < NE) Tg[row * TILE_LD + TILE_M + oc + 1] = c1 + (oc + 1 == NVP ? Tg[STG_GY + row] : 0.0);
+            }
+          }
+        __syncwarp();
+        // Y'[M | g_y + M y0]  and  Y'Yext
+#pragma unroll 1
+        for (int mt = 0; mt < (NVP + 7) / 8; ++mt)
+#pragma unroll 1
+          for (int nt = 0; nt < (NE + 7) / 8; ++nt) {
+            double h0 = 0.0, h1 = 0.0, y0 = 0.0, y1 = 0.0;
+            const int m = mt * 8 + fr, n = nt * 8 + fr;
+#pragma unroll
+            for (int kk = 0; kk < (NY + 3) / 4; ++kk) {
+              const int k = kk * 4 + fq;
+              const double av = (k < NY && m < NVP) ? Tg[k * TILE_LD + NY + m] : 0.0;
+              const double bm = (k < NY && n < NE) ? Tg[k * TILE_LD + TILE_M + n] : 0.0;
+              const double by = (k < NY && n < NE) ? Tg[k * TILE_LD + NY + n] : 0.0;
+              dmma884(h0, h1, av, bm); dmma884(y0, y1, av, by);
+            }
+            if (m < NVP) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int b = nt * 8 + 2 * fq + hh;
+                const double hv = hh ? h1 : h0, yv = hh ? y1 : y0;
+                if (b < NVP) {
+                  double h = Tg[STG_N + m * NE + b] + Tg[STG_N + b * NE + m];
+                  for (int t = DMB_HR_START[m]; t < DMB_HR_START[m + 1]; ++t) if (DMB_HR_COL[t] == b) h += Tg[STG_HNZ + DMB_HR_IDX[t]];
+                  erg[ER_HH + m * NVP + b] = h + hv; erg[ER_YTY + m * NVP + b] = yv;
+                } else if (b == NVP) {
+                  erg[ER_GH + m] = Tg[STG_GOBJ + m] + Tg[STG_N + m * NE + NVP] + hv; erg[ER_YTY0 + m] = yv;
+                }
+              }
+            }
+          }
+        __syncwarp();
+      }
+    }
+    if (act) {
+#else
       // ---- M = (H_yy + Sigma_y) Yext  (rows NY, cols NE) and N = H_vy Yext (rows NVP) via the CSR rows of H ----------
       for (int idx = c.gl; idx < NQ * NE; idx += GSZ) {
         const int rq = idx / NE, a = idx - rq * NE;            // rq < NVP: N row, else M row
@@ -709,6 +824,7 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
         }
         er[ER_GH + a] = g; er[ER_YTY0 + a] = yy;
       }
+#endif
       for (int idx = c.gl; idx < NX * NVP; idx += GSZ) { const int r = idx / NVP; er[ER_AB + idx] = T[DMB_XF_SEL[r] * TILE_LD + NY + idx - r * NVP]; }
       for (int i = c.gl; i < NX; i += GSZ)
         er[ER_B + i] = T[DMB_XF_SEL[i] * TILE_LD + NY + NVP] + (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + i]);
@@ -765,23 +881,6 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
 #else
 #define DMB_TREE_PAR 0
 #define DMB_FLAG_OR(flag, bits) (*(flag) |= (bits))
-#endif
-
-#if !defined(DMB_HOSTSIM) && (DMB_NX + 2 * DMB_NU + DMB_NEPS <= 8) && !defined(DMB_NO_DMMA)
-#define DMB_DMMA_SWEEP 1
-// FP64 tensor-core MMA (sm_100a: DMMA.8x8x4): D(8x8) += A(8x4, row) * B(4x8, col).  Fragments per lane (r = lane / 4,
-// q = lane % 4): A[r][q], B[q][r], C/D[r][2q], C/D[r][2q + 1].
-DMB_DEV void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-// element (row, col) of a matrix held in the C-fragment layout, delivered to the calling lane (row / col may differ per lane)
-DMB_DEV double frag_get(double c0, double c1, int row, int col) {
-  const int src = row * 4 + (col >> 1);
-  const double v0 = __shfl_sync(DMB_FULL, c0, src), v1 = __shfl_sync(DMB_FULL, c1, src);
-  return (col & 1) ? v1 : v0;
-}
-#else
-#define DMB_DMMA_SWEEP 0
 #endif
 
 // lower-triangle index -> (row i >= column j)
