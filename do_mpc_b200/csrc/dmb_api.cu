@@ -35,13 +35,15 @@
 #define ERN_DOUBLES (NEDGE * ER_SZ + NNODE * WN_NODE)
 #define SM_NODE (SM_ER + NEDGE * ER_SZ)
 #define SM_VEC (SM_ER + (DMB_ERN_SMEM ? ERN_DOUBLES : 0))
-#define SM_DOUBLES (SM_VEC + (DMB_VEC_SMEM ? WV_END : 0))
+#define SM_DOUBLES ((SM_VEC + (DMB_VEC_SMEM ? WV_END : 0) + 1) & ~1)
 #define SM_BYTES (SM_DOUBLES * sizeof(double) + sizeof(DmbShared) + 16)
 // per-CTA global workspace slot: bulk per-edge data (+ the iterate vectors when they do not fit on chip)
 #define SLOT_VEC 0
 #define SLOT_ERN (SLOT_VEC + (DMB_VEC_SMEM ? 0 : WV_END))
-#define SLOT_EB (SLOT_ERN + (DMB_ERN_SMEM ? 0 : ERN_DOUBLES))
+#define SLOT_EB ((SLOT_ERN + (DMB_ERN_SMEM ? 0 : ERN_DOUBLES) + 1) & ~1)      // even: edge blocks 16-byte aligned (TMA)
 #define SLOT_DOUBLES (SLOT_EB + NEDGE * EB_SZ)
+static_assert(DMB_NGRP <= 16, "DmbShared holds 16 TMA barriers");
+static_assert(SLOT_DOUBLES % 2 == 0 && EB_SZ % 2 == 0 && TILE_SZ % 2 == 0, "TMA bulk copies need 16-byte aligned tiles and edge blocks");
 
 struct KernelArgs {
   int B;
@@ -67,6 +69,12 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
   I.eb = slot + SLOT_EB;
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
+  I.mbar = S->mbar; I.mphase = S->mphase;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DMB_NGRP; ++i) { mbar_init(S->mbar + i, 1); S->mphase[i] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   while (true) {
     if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
     __syncthreads();
@@ -130,6 +138,12 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_sens_kernel(con
   I.eb = slot + SLOT_EB;
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.relax_fac; I.relax_max = a.relax_max;
+  I.mbar = S->mbar; I.mphase = S->mphase;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DMB_NGRP; ++i) { mbar_init(S->mbar + i, 1); S->mphase[i] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   const size_t nrow = a.mode == 1 ? NU : DMB_NW;
   while (true) {
     if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);

@@ -146,7 +146,8 @@ enum DmbStatus {
 #define STG_INVD (STG_GOBJ + NQ)
 #define STG_PERM (STG_INVD + NY)                       // perm[m] = original row of the m-th pivot (as doubles)
 #define STG_DQ STG_GOBJ                                // recovery phase re-uses that space: dq (NQ), r (NY), jd (NNL)
-#define TILE_SZ (STG_PERM + NY)
+#define TILE_SZ ((STG_PERM + NY + 1) & ~1)             // even: every tile starts 16-byte aligned (TMA bulk copies)
+#define IMG_SZ ((NY * TILE_LD + 1) & ~1)                // tile image [LU | Yext | ..] saved to / loaded from the slot in one bulk copy
 static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY >= NNL");
 
 // per-edge reduced data kept in shared memory (inputs of the Riccati sweep)
@@ -158,10 +159,10 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define ER_YTY0 (ER_GH + NVP)                          // Y'y0
 #define ER_SZ (ER_YTY0 + NVP)
 // per-edge bulk data in the per-CTA global slot (coalesced group access only)
-#define EB_LU 0
-#define EB_PIV (EB_LU + NY * NY)
-#define EB_Y (EB_PIV + NY)                             // Yext = [Y | y0], NY x NE row-major
-#define EB_JNZ (EB_Y + NY * NE)
+#define EB_IMG 0                                       // image of the tile rows [0, NY): LU factors (reciprocal pivots on the
+                                                       // diagonal) in columns [0, NY), Yext = [Y | y0] in columns [NY, NY + NE)
+#define EB_PIV (EB_IMG + IMG_SZ)
+#define EB_JNZ (EB_PIV + NY)
 #define EB_HNZ (EB_JNZ + DMB_NNZ_J)
 #define EB_DNZ (EB_HNZ + DMB_NNZ_H)                    // scaled inequality Jacobian nonzeros
 #define EB_GOBJ (EB_DNZ + DMB_NNZ_D)                   // edge-local objective gradient wrt q (NQ)
@@ -171,7 +172,7 @@ static_assert(NY >= NNL, "recovery scratch overlays the factor scratch: needs NY
 #define EB_SIGS (EB_SIGY + NY)
 #define EB_RD (EB_SIGS + NNL)
 #define EB_GY2 (EB_RD + NNL)                           // y-part of the refinement right-hand side (NY)
-#define EB_SZ (EB_GY2 + NY)
+#define EB_SZ ((EB_GY2 + NY + 1) & ~1)                 // even: every edge block starts 16-byte aligned
 // per-node data in shared memory.  Q (NV x NV, v-space) is assembled in parallel (node terms + projected edge
 // Hessians), completed and reduced in place by the sweep: afterwards its leading NXI x NXI block (stride NV) is P.
 #define WN_Q 0                                          // Q / P (NV x NV)
@@ -235,6 +236,8 @@ struct Inst {
   // restoration problem (see resto_terms), zeta = sqrt(mu); the reference point of its proximal term is kept in go / s2
   double zeta;
   int resto;
+  unsigned long long* mbar;   // one mbarrier per lane group (TMA loads of the tile image), shared memory
+  int* mphase;                // its current phase parity
 };
 // restoration problem  min zeta/2 |D_R (v - v_R)|^2 - mu log(v - lo) - mu log(hi - v), D_R = 1/max(1,|v_R|): diagonal Hessian
 // entry and gradient of one variable (primal barrier: no multipliers involved)
@@ -249,7 +252,7 @@ DMB_DEV void bind_vectors(Inst& I, double* vec) {
   I.gl = vec + WV_GL; I.go = vec + WV_GO;
   I.lam = vec + WV_LAM; I.lamn = vec + WV_LAMN; I.lamr = vec + WV_LAMR; I.res = vec + WV_RES; I.rest = vec + WV_REST; I.dc = vec + WV_DC;
   I.s = vec + WV_S; I.st = vec + WV_ST; I.ds = vec + WV_DS; I.vU = vec + WV_VU; I.s2 = vec + WV_S2; I.soc = vec + WV_SOC;
-  I.zeta = 0.0; I.resto = 0;
+  I.zeta = 0.0; I.resto = 0; I.mbar = nullptr; I.mphase = nullptr;
 }
 DMB_DEV const double* p_tvp_at(const double* p, int k) { return p + DMB_P_TVP + k * DMB_NTVP; }
 
@@ -351,6 +354,40 @@ DMB_DEV double frag_get(double c0, double c1, int row, int col) {
 #else
 #define DMB_DMMA_FACTOR 0
 #define DMB_DMMA_SWEEP 0
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) between a lane group's tile and its image in the per-CTA slot: one
+// instruction by one lane moves the whole [LU | Yext] image (2.6 KB for cfg #2) instead of ~15 LDG + STS per lane, and the
+// factor phase keeps computing while the store drains.  One mbarrier per lane group tracks the loads.
+// ---------------------------------------------------------------------------------------------------
+#ifndef DMB_HOSTSIM
+#define DMB_TMA 1
+DMB_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DMB_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DMB_DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned m = smem_u32(bar);
+  asm volatile("fence.proxy.async;" ::: "memory");                     // earlier generic writes of the image (y0 column) -> async proxy
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
+}
+DMB_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// smem -> global; returns when the source may be overwritten (the write itself is awaited by tma_store_drain)
+DMB_DEV void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes of the tile -> visible to the async proxy
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+DMB_DEV void tma_store_drain() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#else
+#define DMB_TMA 0
 #endif
 
 // batched copy: all loads of a lane are issued before the first store (the two pointers may alias for the
@@ -673,10 +710,6 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     SUB_TICK(I, 1);
     if (act) {
       for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
-      for (int idx = c.gl; idx < NY * NY; idx += GSZ) {
-        const int r = idx / NY, cc = idx - r * NY;
-        eb[EB_LU + idx] = r == cc ? T[STG_INVD + r] : T[r * TILE_LD + cc];
-      }
       // ---- back substitution, one lane per right-hand side; then Yext = [-X | x_rhs] --------------------------------
       for (int j = c.gl; j < NE; j += GSZ) {
         for (int k = NY - 1; k >= 0; --k) {
@@ -690,7 +723,19 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     WARP_SYNC();
     SUB_TICK(I, 2);
     if (act) {
-      for (int idx = c.gl; idx < NY * NE; idx += GSZ) { const int r = idx / NE; eb[EB_Y + idx] = T[r * TILE_LD + NY + idx - r * NE]; }
+      // tile image [LU (reciprocal pivots on the diagonal) | Yext] -> slot
+      for (int i = c.gl; i < NY; i += GSZ) T[i * TILE_LD + i] = T[STG_INVD + i];
+    }
+    WARP_SYNC();
+    if (act) {
+#if DMB_TMA
+      if (c.gl == 0) tma_store_1d(eb + EB_IMG, T, IMG_SZ * 8);
+#else
+      for (int i = c.gl; i < IMG_SZ; i += GSZ) eb[EB_IMG + i] = T[i];
+#endif
+    }
+    WARP_SYNC();
+    if (act) {
 #if DMB_DMMA_FACTOR
     }
     // ---- projection products on the FP64 tensor cores (DMMA.8x8x4) ---------------------------------------------------------
@@ -855,6 +900,9 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     WARP_SYNC();
 #endif
   }
+#if DMB_TMA
+  tma_store_drain();                 // the tile images are in the slot before any group loads them back
+#endif
   CTA_SYNC();
 }
 
@@ -1233,6 +1281,18 @@ DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double k
   riccati_backward_t<false>(c, I, mu, kappa_d, delta, ls_mode, Qs, flag);
 }
 
+// tile image of edge block `eb` -> the group's tile T (all lanes of the group call; returns when the data has landed)
+DMB_DEV void load_tile_image(const Ctx& c, const Inst& I, const double* eb, double* T, bool act) {
+#if DMB_TMA
+  if (act && c.gl == 0) tma_load_1d(T, eb + EB_IMG, IMG_SZ * 8, I.mbar + c.grp);
+  if (act) mbar_wait(I.mbar + c.grp, (unsigned)I.mphase[c.grp]);
+  WARP_SYNC();
+  if (act && c.gl == 0) I.mphase[c.grp] ^= 1;
+#else
+  if (act) for (int i = c.gl; i < IMG_SZ; i += GSZ) T[i] = eb[EB_IMG + i];
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward roll-out (warp 0) then, per edge by its lane group: dy = Yext [dv; 1], new multipliers by a
 // transposed LU solve in the group tile, inequality steps.
@@ -1337,10 +1397,11 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
     const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+#if DMB_TMA
+    if (act && c.gl == 0) tma_load_1d(T, eb + EB_IMG, IMG_SZ * 8, I.mbar + c.grp);       // [LU | Yext] image: one bulk copy in flight
+#endif
     if (act) {
-      // stage LU, Yext and the sparse data of this edge (coalesced, independent loads)
-      DMB_COPY_BATCH(NY * NY, c.gl, GSZ, eb[EB_LU + idx], T[(idx / NY) * TILE_LD + idx % NY] = val);
-      DMB_COPY_BATCH(NY * NE, c.gl, GSZ, eb[EB_Y + idx], T[(idx / NE) * TILE_LD + NY + idx % NE] = val);
+      // stage the sparse data of this edge (coalesced, independent loads) while the image lands
       DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[gy_off + idx], T[STG_GY + idx] = val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
@@ -1360,7 +1421,14 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
         I.lamn[LAM_EDGE(e) + NY + a] = s;
       }
     }
+#if DMB_TMA
+    if (act) mbar_wait(I.mbar + c.grp, (unsigned)I.mphase[c.grp]);
     WARP_SYNC();
+    if (act && c.gl == 0) I.mphase[c.grp] ^= 1;
+#else
+    if (act) for (int i = c.gl; i < IMG_SZ; i += GSZ) T[i] = eb[EB_IMG + i];
+    WARP_SYNC();
+#endif
     if (act) {
       for (int i = c.gl; i < NY; i += GSZ) {
         double s = T[i * TILE_LD + NY + NVP];

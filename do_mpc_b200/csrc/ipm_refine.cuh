@@ -160,7 +160,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
 // ---------------------------------------------------------------------------------------------------
 // right-hand-side dependent part of the edge elimination for a new rhs (rd = I.gl, rp = I.rest), using the stored
 // LU / Y: y0 = -G_y^{-1} rp_G, reduced gradient, Y'y0, b.  One lane group per edge, data staged in the tile.
-// Overwrites ER_GH / ER_YTY0 / ER_B, the y0 column of EB_Y and EB_GY (:= rd_y) — the primary values are no longer
+// Overwrites ER_GH / ER_YTY0 / ER_B, the y0 column of the tile image (EB_IMG) and EB_GY (:= rd_y) — the primary values are no longer
 // needed once the primary step has been recovered (the primary g_y in EB_GY is kept for further residual evaluations).
 // ---------------------------------------------------------------------------------------------------
 DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
@@ -174,12 +174,11 @@ DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
     double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
     double* er = I.er + (size_t)(act ? e : 0) * ER_SZ;
     if (act) {
-      DMB_COPY_BATCH(NY * NY, c.gl, GSZ, eb[EB_LU + idx], T[(idx / NY) * TILE_LD + idx % NY] = val);
-      DMB_COPY_BATCH(NY * NE, c.gl, GSZ, eb[EB_Y + idx], T[(idx / NE) * TILE_LD + NY + idx % NE] = val);
       DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = val);
       DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
       for (int m = c.gl; m < NY; m += GSZ) bv[m] = rp[LAM_EDGE(e) + (int)eb[EB_PIV + m]];      // P rp_G
     }
+    load_tile_image(c, I, eb, T, act);                 // [LU | Yext] image (one TMA bulk copy)
     WARP_SYNC();
     // L b' = P rp_G (unit lower), U x = b' (reciprocal diagonal): column sweeps, lanes over rows
     for (int k = 0; k < NY; ++k) {
@@ -231,7 +230,7 @@ DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
         er[ER_GH + a] = g; er[ER_YTY0 + a] = yy;
       }
       for (int i = c.gl; i < NX; i += GSZ) er[ER_B + i] = bv[DMB_XF_SEL[i]] + rp[LAM_EDGE(e) + NY + i];
-      for (int j = c.gl; j < NY; j += GSZ) { eb[EB_Y + j * NE + NVP] = bv[j]; eb[EB_GY2 + j] = rd[EDGE_OFF(e) + j]; }
+      for (int j = c.gl; j < NY; j += GSZ) { eb[EB_IMG + j * TILE_LD + NY + NVP] = bv[j]; eb[EB_GY2 + j] = rd[EDGE_OFF(e) + j]; }
     }
     WARP_SYNC();
   }

@@ -13,6 +13,8 @@ struct DmbShared {          // small per-CTA state in shared memory
   double filt_theta[MAX_FILTER], filt_phi[MAX_FILTER];
   int n_filt;
   int flag, fail;
+  int mphase[16];                      // phase parity of the lane groups' TMA barriers
+  unsigned long long mbar[16];         // one mbarrier per lane group (tile-image loads, see load_tile_image)
 };
 
 #define DMB_NPHASE 17
