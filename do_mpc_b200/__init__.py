@@ -29,6 +29,6 @@ class _NS:
 model = _NS(Model=_model_mod.Model)
 controller = _NS(MPC=_controller_mod.MPC, MPCSettings=_controller_mod.MPCSettings)
 simulator = _NS(Simulator=_sim_mod.Simulator)
-estimator = _NS(StateFeedback=_est_mod.StateFeedback, Estimator=_est_mod.Estimator)
+estimator = _NS(StateFeedback=_est_mod.StateFeedback, Estimator=_est_mod.Estimator, MHE=_est_mod.MHE, MHESettings=_est_mod.MHESettings)
 differentiator = _NS(DoMPCDifferentiator=_diff_mod.DoMPCDifferentiator, NLPDifferentiatorSettings=_diff_mod.NLPDifferentiatorSettings,
                      NLPDifferentiatorStatus=_diff_mod.NLPDifferentiatorStatus, indexf=_diff_mod.indexf)

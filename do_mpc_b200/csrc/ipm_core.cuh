@@ -123,6 +123,16 @@ enum DmbStatus {
 #define LAM_EDGE(e) (NX + (e) * NLE)
 #define DMB_INF 1e19
 #define MAX_FILTER 32
+// partially free root (moving-horizon estimation: the whole root state; nl_cons_single_slack: the lifted slack): the LAST
+// DMB_NFREE0 components of the root state are decision variables without an initial-condition row; the root may carry its
+// own cost term (MHE arrival cost, gen_arrival*).  NXF = number of root components fixed by x0.
+#ifndef DMB_NFREE0
+#define DMB_NFREE0 0
+#endif
+#ifndef DMB_HAS_ARRIVAL
+#define DMB_HAS_ARRIVAL 0
+#endif
+#define NXF (NX - DMB_NFREE0)
 
 // lane groups: one group factorises one edge
 #ifdef DMB_HOSTSIM
@@ -498,8 +508,11 @@ DMB_PHASE void eval_point(const Ctx& c, const Inst& I, const double* w, const do
 #pragma unroll
     for (int i = 0; i < NU; ++i) up[i] = node_uprev(I, w, n, i);
     f += NODE_RW_OF(n) * gen_rterm(w + NODE_OFF(n) + NX, up, I.p + DMB_P_TVP + NODE_K_OF(n) * DMB_NTVP);
+#if DMB_HAS_ARRIVAL
+    if (n == 0) f += gen_arrival(w + NODE_OFF(0), p_tvp_at(I.p, 0), I.p + DMB_P_P);
+#endif
   }
-  for (int i = c.tid; i < NX; i += c.nthr) res[i] = w[NODE_OFF(0) + i] - I.p[DMB_P_X0 + i] * DMB_INV_XSCALE[i];
+  for (int i = c.tid; i < NX; i += c.nthr) res[i] = i < NXF ? w[NODE_OFF(0) + i] - I.p[DMB_P_X0 + i] * DMB_INV_XSCALE[i] : 0.0;
   CTA_SYNC();
   double th = 0.0, mx = 0.0;
   for (int i = c.tid; i < NLAM; i += c.nthr) { const double a = fabs(res[i]); th += a; mx = fmax(mx, a); }
@@ -575,7 +588,14 @@ DMB_PHASE void eval_derivatives(const Ctx& c, const Inst& I) {
           gen_mterm_grad(w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), gm);
           go += I.df * EDGE_OMEGA_OF(pe) * gm[i];
         }
-      } else gc += I.lam[i];
+      } else {
+        gc += I.lam[i];
+#if DMB_HAS_ARRIVAL
+        double ga[NX];
+        gen_arrival_grad(w + NODE_OFF(0), p_tvp_at(I.p, 0), I.p + DMB_P_P, ga);
+        go += I.df * ga[i];
+#endif
+      }
     } else if (i < NX + NU) {
       const int iu = i - NX;
       go += I.node[(size_t)n * WN_NODE + WN_RG + iu];
@@ -830,15 +850,25 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     if (act) {
 #else
       // ---- M = (H_yy + Sigma_y) Yext  (rows NY, cols NE) and N = H_vy Yext (rows NVP) via the CSR rows of H ----------
+      // DMB_EMU_FP32_PROJ (experiment, tools/plan_a_experiment.py): the projection products with FP32 operands and FP32
+      // accumulation — the accuracy a TF32x3-split tcgen05 product reaches at best — to measure what the FP64 refinement
+      // loop can absorb (north_star plan A).  Never defined in product builds.
+#ifdef DMB_EMU_FP32_PROJ
+#define DMB_PACC float
+#define DMB_PMUL(x, y) ((float)(x) * (float)(y))
+#else
+#define DMB_PACC double
+#define DMB_PMUL(x, y) ((x) * (y))
+#endif
       for (int idx = c.gl; idx < NQ * NE; idx += GSZ) {
         const int rq = idx / NE, a = idx - rq * NE;            // rq < NVP: N row, else M row
-        double s = 0.0;
+        DMB_PACC s = 0.0;
         for (int t = DMB_HR_START[rq]; t < DMB_HR_START[rq + 1]; ++t) {
           const int cq = DMB_HR_COL[t];
-          if (cq >= NVP) s += T[STG_HNZ + DMB_HR_IDX[t]] * T[(cq - NVP) * TILE_LD + NY + a];
+          if (cq >= NVP) s += DMB_PMUL(T[STG_HNZ + DMB_HR_IDX[t]], T[(cq - NVP) * TILE_LD + NY + a]);
         }
         if (rq >= NVP) {
-          s += T[STG_SIGY + rq - NVP] * T[(rq - NVP) * TILE_LD + NY + a];
+          s += DMB_PMUL(T[STG_SIGY + rq - NVP], T[(rq - NVP) * TILE_LD + NY + a]);
           T[(rq - NVP) * TILE_LD + TILE_M + a] = s;
         } else T[STG_N + rq * NE + a] = s;
       }
@@ -851,12 +881,14 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
         const int a = idx / NVP, b = idx - a * NVP;
         double h = T[STG_N + a * NE + b] + T[STG_N + b * NE + a], yty = 0.0;
         for (int t = DMB_HR_START[a]; t < DMB_HR_START[a + 1]; ++t) if (DMB_HR_COL[t] == b) h += T[STG_HNZ + DMB_HR_IDX[t]];
+        DMB_PACC hp = 0.0;
 #pragma unroll 4
         for (int j = 0; j < NY; ++j) {
           const double yja = T[j * TILE_LD + NY + a];
-          h += yja * T[j * TILE_LD + TILE_M + b];
+          hp += DMB_PMUL(yja, T[j * TILE_LD + TILE_M + b]);
           yty += yja * T[j * TILE_LD + NY + b];
         }
+        h += hp;
         er[ER_HH + idx] = h; er[ER_YTY + idx] = yty;
       }
       for (int a = c.gl; a < NVP; a += GSZ) {
@@ -1021,6 +1053,12 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
         if (!ls_mode) { double hm[NX * NX]; gen_mterm_hess(I.w + NODE_OFF(n), p_tvp_at(I.p, NHOR), edge_pp(I.p, pe), hm); val += wgt * hm[a * NX + b]; }
       }
     } else {
+#if DMB_HAS_ARRIVAL
+      if (n == 0 && a < NX && b < NX) {
+        if (diag) { double ga[NX]; gen_arrival_grad(I.w + NODE_OFF(0), p_tvp_at(I.p, 0), I.p + DMB_P_P, ga); gq += I.df * ga[a]; }
+        if (!ls_mode) { double ha[NX * NX]; gen_arrival_hess(I.w + NODE_OFF(0), p_tvp_at(I.p, 0), I.p + DMB_P_P, ha); val += I.df * ha[a * NX + b]; }
+      }
+#endif
       // rterm couples u (v-pos NXI..) and u_prev (v-pos NX..)
       const int ra = (a >= NXI && a < NXI + NU) ? a - NXI : ((a >= NX && a < NXI) ? NU + a - NX : -1);
       if (diag && ra >= 0) gq += wn[WN_RG + ra];
@@ -1274,11 +1312,51 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
     }
     SUB_TICK(I, 5);
   }
+#if DMB_NFREE0 > 0
+  // free root components: in-place Cholesky of P_0[f, f] (lower triangle, reciprocal diagonal); positive definiteness is part
+  // of the inertia test.  The roll-outs solve  P_0[f,f] d xi_f = -(p_0[f] + P_0[f, fixed] d xi_fixed)  with it.
+  if (!LDL && c.warp == 0) {
+    WARP_SYNC();
+    if (c.lane == 0) {
+      double* w0 = I.node;
+      int bad = 0;
+      for (int a = 0; a < DMB_NFREE0; ++a)
+        for (int b = 0; b <= a; ++b) {
+          double sv = P_AT(w0, NXF + a, NXF + b);
+          for (int t = 0; t < b; ++t) sv -= P_AT(w0, NXF + a, NXF + t) * P_AT(w0, NXF + b, NXF + t);
+          if (a == b) { if (!(sv > 0.0)) { bad = 1; sv = 1.0; } P_AT(w0, NXF + a, NXF + a) = rsqrt(sv); }
+          else P_AT(w0, NXF + a, NXF + b) = sv * P_AT(w0, NXF + b, NXF + b);
+        }
+      if (bad) DMB_FLAG_OR(flag, bad);
+    }
+    WARP_SYNC();
+  }
+#endif
   CTA_SYNC();
 }
 
 DMB_PHASE void riccati_backward(const Ctx& c, const Inst& I, double mu, double kappa_d, double delta, int ls_mode, double* Qs, int* flag) {
   riccati_backward_t<false>(c, I, mu, kappa_d, delta, ls_mode, Qs, flag);
+}
+
+// root state step d xi_0 (NXI entries into wn0[WN_DXI]): fixed components from the initial-condition residual, free components
+// (DMB_NFREE0 > 0) from the Cholesky factor left in P_0[f, f] by riccati_backward.  Called by lane 0 of warp 0.
+DMB_DEV void root_step(double* w0, const double* res) {
+  for (int a = 0; a < NXI; ++a) w0[WN_DXI + a] = a < NXF ? -res[a] : 0.0;
+#if DMB_NFREE0 > 0
+  double y[DMB_NFREE0];
+  for (int a = 0; a < DMB_NFREE0; ++a) {                       // rhs = -(p_f + P[f, fixed] dxi_fixed), then L y = rhs
+    double sv = -w0[WN_QV + NXF + a];
+    for (int t = 0; t < NXF; ++t) sv -= P_AT(w0, t, NXF + a) * w0[WN_DXI + t];        // P symmetric: P[f][t] = P[t][f]
+    for (int t = 0; t < a; ++t) sv -= P_AT(w0, NXF + a, NXF + t) * y[t];
+    y[a] = sv * P_AT(w0, NXF + a, NXF + a);
+  }
+  for (int a = DMB_NFREE0 - 1; a >= 0; --a) {                  // L' x = y
+    double sv = y[a];
+    for (int t = a + 1; t < DMB_NFREE0; ++t) sv -= P_AT(w0, NXF + t, NXF + a) * w0[WN_DXI + NXF + t];
+    w0[WN_DXI + NXF + a] = sv * P_AT(w0, NXF + a, NXF + a);
+  }
+#endif
 }
 
 // tile image of edge block `eb` -> the group's tile T (all lanes of the group call; returns when the data has landed)
@@ -1308,7 +1386,13 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     // store -> load round trip per node, ~1.2k cycles; r2 profile gpurun_out/r2d_r1_prof.json: fwd_sweep 7.6 % of the cycles)
     if (c.warp == 0) {
       const int t = c.lane;
+#if DMB_NFREE0 > 0
+      if (t == 0) root_step(I.node, res);
+      WARP_SYNC();
+      double dxi = t < NXI ? I.node[WN_DXI + t] : 0.0;
+#else
       double dxi = t < NX ? -res[t] : 0.0;
+#endif
       for (int n = 0; n <= NHOR; ++n) {
         double* wn = I.node + (size_t)n * WN_NODE;
         double* dwn = I.dw + NODE_OFF(n);
@@ -1348,7 +1432,11 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
       double* wn = I.node + (size_t)n * WN_NODE;
       const int k = lvl;
       if (n == 0) {
+#if DMB_NFREE0 > 0
+        if (c.lane == 0) root_step(wn, res);
+#else
         for (int a = c.lane; a < NXI; a += DMB_LANES) wn[WN_DXI + a] = a < NX ? -res[a] : 0.0;
+#endif
         WARP_SYNC();
       }
       double* dwn = I.dw + NODE_OFF(n);
@@ -1383,8 +1471,8 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
       const double* w0 = I.node;
       for (int a = c.lane; a < NX; a += DMB_LANES) {
         double s = w0[WN_QV + a];
-        for (int t = 0; t < NXI; ++t) s += P_AT(w0, a, t) * w0[WN_DXI + t];
-        I.lamn[a] = -s;
+        for (int t = 0; t < NXI; ++t) s += P_AT(w0, a, t) * w0[WN_DXI + t];      // (rows of fixed components: untouched by the root Cholesky)
+        I.lamn[a] = a < NXF ? -s : 0.0;                                          // free root components have no initial-condition row
       }
     }
     SUB_TICK(I, 6);

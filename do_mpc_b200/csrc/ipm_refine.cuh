@@ -127,7 +127,14 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
           const double wgt = I.df * EDGE_OMEGA_OF(pe);
           for (int b = 0; b < NX; ++b) r += wgt * hm[i * NX + b] * I.dw[NODE_OFF(n) + b];
         }
-      } else r += I.lamn[i];
+      } else {
+        r += I.lamn[i];
+#if DMB_HAS_ARRIVAL
+        double ha[NX * NX];
+        gen_arrival_hess(I.w + NODE_OFF(0), p_tvp_at(I.p, 0), I.p + DMB_P_P, ha);
+        for (int b = 0; b < NX; ++b) r += I.df * ha[i * NX + b] * I.dw[NODE_OFF(0) + b];
+#endif
+      }
     } else if (i < NX + NU) {
       const int iu = i - NX;
       // own rterm: rows of u ; children's rterm: rows of their u_prev = this u
@@ -148,7 +155,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
     nrm_rho = fmax(nrm_rho, fabs(r));
   }
   for (int i = c.tid; i < NX; i += c.nthr) {
-    const double r = res[i] + I.dw[NODE_OFF(0) + i];
+    const double r = i < NXF ? res[i] + I.dw[NODE_OFF(0) + i] : 0.0;      // free root components have no initial-condition row
     rp[i] = r;
     nrm_rho = fmax(nrm_rho, fabs(r));
   }

@@ -669,6 +669,11 @@ DMB_DEV void load_initial_guess(const Ctx& c, const double* x_flat, const double
     dst[i] = v;
   }
   CTA_SYNC();
+#if DMB_HAS_INIT_FROM
+  // lifted copies of a global variable (MHE: the estimated parameters at every node) start from the value of the original
+  for (int i = c.tid; i < NWI; i += c.nthr) if (DMB_W_INIT_FROM[i] >= 0) dst[i] = dst[DMB_W_INIT_FROM[i]];
+  CTA_SYNC();
+#endif
 }
 
 // solution -> flat arrays.  x_out must already hold the initial guess (unused reference variables keep it).

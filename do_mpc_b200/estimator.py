@@ -18,6 +18,9 @@ class Estimator:
     def reset_history(self): self.data.init_storage()
 
 
+from .mhe import MHE, MHESettings  # noqa: E402,F401  (moving horizon estimator: do_mpc_b200/mhe.py)
+
+
 class StateFeedback(Estimator):
     def make_step(self, y0):
         return y0

@@ -48,6 +48,10 @@ class Model:
             shape = (shape, 1)
         if len(shape) == 1:
             shape = (shape[0], 1)
+        # long names are accepted like the reference does (model/_model.py:598-604)
+        for long_name, short in (("states", "_x"), ("inputs", "_u"), ("algebraic", "_z"), ("parameter", "_p"), ("timevarying_parameter", "_tvp")):
+            if var_type == long_name:
+                var_type = short
         if not var_type.startswith("_"):
             var_type = "_" + var_type
         if var_type not in _VAR_TYPES:

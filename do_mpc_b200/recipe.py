@@ -66,6 +66,14 @@ class Recipe:
     xf_sel: np.ndarray = None   # indices inside y of the end-of-interval state (E y = x_child)
     x_scaling: np.ndarray = None; u_scaling: np.ndarray = None; z_scaling: np.ndarray = None
     opt_x_scaling: np.ndarray = None
+    # ---- generalisations used by the moving-horizon estimator / lifted global variables (do_mpc_b200/mhe.py) ----------------
+    n_free0: int = 0             # the LAST n_free0 components of the root state are free (no initial-condition row)
+    arrival: SX = None           # root cost term in the root-state symbols `x0sym` (MHE arrival cost), with tvp / pp
+    x0sym: SX = None
+    w2flat: np.ndarray = None    # explicit internal -> flat opt_x map (NWI entries, -1 = no flat counterpart); None: MPC layout
+    lam2flat: np.ndarray = None  # explicit internal multiplier row -> flat g row map (NLAM entries)
+    w_init_from: np.ndarray = None   # initial value of an entry without flat counterpart: copy of another internal entry (-1: none)
+    has_dummies: bool = None     # opt_x holds variables that appear nowhere (IPOPT's delta_w schedule is mimicked); None: MPC rule
 
 
 def build_recipe(mpc) -> Recipe:

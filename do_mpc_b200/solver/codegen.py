@@ -185,6 +185,22 @@ def generate(r: Recipe) -> str:
     out.append(_fn("gen_mterm_hess", m_args + ", double* __restrict__ hm",
                    "  (void)x; (void)tvp; (void)pp;\n" +
                    E.emit_c([(f"hm[{i * r.n_x + j}]", HM[i][j]) for i in range(r.n_x) for j in range(r.n_x)], inpM)))
+    # ---- root cost (MHE arrival cost) in the root-state symbols ------------------------------------------------------------------
+    if r.arrival is not None:
+        x0_ids = r.x0sym.ids()
+        inpA = {}
+        for i, s_ in enumerate(x0_ids): inpA[s_] = f"x[{i}]"
+        for i, s_ in enumerate(tv_ids): inpA[s_] = f"tvp[{i}]"
+        for i, s_ in enumerate(pp_ids): inpA[s_] = f"pp[{i}]"
+        ar = r.arrival.ids()[0]
+        gA = E.gradient(ar, x0_ids)
+        HA = [E.gradient(g_, x0_ids) for g_ in gA]
+        out.append(_fn("gen_arrival", m_args, "  (void)x; (void)tvp; (void)pp;\n  double r;\n" + E.emit_c([("r", ar)], inpA) + "\n  return r;", "double"))
+        out.append(_fn("gen_arrival_grad", m_args + ", double* __restrict__ ga",
+                       "  (void)x; (void)tvp; (void)pp;\n" + E.emit_c([(f"ga[{i}]", e) for i, e in enumerate(gA)], inpA)))
+        out.append(_fn("gen_arrival_hess", m_args + ", double* __restrict__ ha",
+                       "  (void)x; (void)tvp; (void)pp;\n" +
+                       E.emit_c([(f"ha[{i * r.n_x + j}]", HA[i][j]) for i in range(r.n_x) for j in range(r.n_x)], inpA)))
     # ---- parameter derivatives for the sensitivity right-hand sides (differentiator, _nlpdifferentiator.py:289-304) -------------
     def switch(cases):
         if not cases:
@@ -214,7 +230,7 @@ def generate(r: Recipe) -> str:
     # ---- header with dimensions and tables ------------------------------------------------------------------------------------------------
     n_node = len(r.node_k)
     node_rw = [1.0 / r.n_scenarios[k] if k < r.N else 0.0 for k in r.node_k]
-    has_dummies = int((r.P > 0) or (r.n_comb ** r.n_robust > 1))
+    has_dummies = int((r.P > 0) or (r.n_comb ** r.n_robust > 1)) if r.has_dummies is None else int(r.has_dummies)
     H: List[str] = []
     H.append("// GENERATED by do_mpc_b200.solver.codegen — do not edit.")
     H.append("#pragma once")
@@ -223,7 +239,7 @@ def generate(r: Recipe) -> str:
                 NY=r.n_y, NNODE=n_node, NEDGE=len(r.edge_k), NHOR=r.N, NW=r.n_w, NG=r.n_g, NP=r.n_p,
                 NAUX=len(aux_ids), DISCRETE=int(r.discrete), P_X0=r.p_x0, P_TVP=r.p_tvp, P_P=r.p_p, P_UPREV=r.p_uprev,
                 NNZ_J=len(jn), NNZ_H=len(hn), NNZ_D=len(dn), HAS_DUMMIES=has_dummies, NPZ=r.Pz, NPC=r.P,
-                NSCEN=r.n_comb ** r.n_robust, NTHETA=n_th)
+                NSCEN=r.n_comb ** r.n_robust, NTHETA=n_th, NFREE0=r.n_free0, HAS_ARRIVAL=int(r.arrival is not None))
     for k, v in dims.items():
         H.append(f"#define DMB_{k} {v}")
     H.append(f"#define NLAM_ACTIVE {r.n_g}")
@@ -286,7 +302,13 @@ def generate(r: Recipe) -> str:
             l2f += [g0 + r.n_z + r.n_x + i for i in range(n_nl)]
         else:
             l2f += [g0 + i for i in range(r.n_y + r.n_x + n_nl)]
-    assert len(w2f) == n_node * n_vp + n_edge * r.n_y
+    if r.w2flat is not None:
+        w2f, l2f = [int(v) for v in r.w2flat], [int(v) for v in r.lam2flat]
+        assert len(l2f) == r.n_x + n_edge * (r.n_y + r.n_x + n_nl), (len(l2f), r.n_x + n_edge * (r.n_y + r.n_x + n_nl))
+    assert len(w2f) == n_node * n_vp + n_edge * r.n_y, (len(w2f), n_node * n_vp + n_edge * r.n_y)
+    init_from = [-1] * len(w2f) if r.w_init_from is None else [int(v) for v in r.w_init_from]
+    H.append(f"#define DMB_HAS_INIT_FROM {int(any(v >= 0 for v in init_from))}")
+    H.append(_ctab("int", "DMB_W_INIT_FROM", init_from if any(v >= 0 for v in init_from) else [0]))
     H.append("#define DMB_W2FLAT_INIT {" + ", ".join(str(v) for v in w2f) + "}")
     H.append("#define DMB_LAM2FLAT_INIT {" + ", ".join(str(v) for v in l2f) + "}")
     H.append(f"DMB_TABLE const int DMB_W2FLAT[{len(w2f)}] = DMB_W2FLAT_INIT;")

@@ -203,6 +203,9 @@ class IPMSolver:
             for k in range(nlp.ix_eps.shape[0]):
                 for s_ in range(S):
                     vb[nlp.ix_eps[k, s_]] = nid(k, s_)
+        if hasattr(nlp, "partition_extra"):
+            for idx, (k, s_) in nlp.partition_extra():
+                vb[np.asarray(idx)] = nid(k, s_)
         gb = np.zeros(nlp.n_g, dtype=np.int64)                     # node of every constraint row (init rows: root)
         starts = [e[4] for e in nlp.edges] + [nlp.n_g]
         for (k, s_, b, ch, row), nxt in zip(nlp.edges, starts[1:]):

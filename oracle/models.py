@@ -224,3 +224,42 @@ def industrial_poly(n_horizon=20, n_robust=1):
                   x_lb=[0.0, 0.0, 26.0, 363.15 - tr, 298.0, 298.0, 288.0, 288.0, 0.0, -inf], x_ub=x_ub,
                   u_lb=[0.0, 333.15, 333.15], u_ub=[3.0e4, 373.15, 373.15], nl_cons=nl,
                   p_scenarios=_scenarios([950.0, 950.0 * 1.30, 950.0 * 0.70], [7.0, 7.0 * 1.30, 7.0 * 0.70]))
+
+
+# ------------------------------------------------------------------------------------------------
+def rotating_masses_mhe(n_horizon=10):
+    """examples/rotating_oscillating_masses_mhe_mpc/template_{model,mhe}.py: 8 states, 2 inputs, 5 noisy measurements,
+    Theta_1 estimated, default objective with P_x = 1e-4 I, P_v = tvp, P_p = p, two hard constraints on Theta_1 at all
+    collocation points."""
+    from .mhe import MHEDef
+    phi = sy.symbols("phi_1 phi_2 phi_3")
+    dphi = sy.symbols("dphi_0 dphi_1 dphi_2")
+    phi_m = sy.symbols("phi_m_0 phi_m_1")
+    u = sy.symbols("phi_m_set_0 phi_m_set_1")
+    phi_2_set = sy.Symbol("phi_2_set")
+    P_v = sy.symbols("P_v_0:25")                      # 5 x 5, column-major like CasADi's vec (symmetric here)
+    P_p = sy.Symbol("P_p")
+    T1, T2, T3 = sy.symbols("Theta_1 Theta_2 Theta_3")
+    c = np.array([2.697, 2.66, 3.05, 2.86]) * 1e-3
+    d = np.array([6.78, 8.01, 8.82]) * 1e-5
+    tau = 1e-2
+    rhs = [dphi[0], dphi[1], dphi[2],
+           -c[0] / T1 * (phi[0] - phi_m[0]) - c[1] / T1 * (phi[0] - phi[1]) - d[0] / T1 * dphi[0],
+           -c[1] / T2 * (phi[1] - phi[0]) - c[2] / T2 * (phi[1] - phi[2]) - d[1] / T2 * dphi[1],
+           -c[2] / T3 * (phi[2] - phi[1]) - c[3] / T3 * (phi[2] - phi_m[1]) - d[2] / T3 * dphi[2],
+           1 / tau * (u[0] - phi_m[0]), 1 / tau * (u[1] - phi_m[1])]
+    x = list(phi) + list(dphi) + list(phi_m)
+    m = ModelDef("continuous", x=x, u=list(u), tvp=[phi_2_set] + list(P_v), p=[P_p, T1, T2, T3], rhs=rhs)
+    v = list(sy.symbols("v_0:5"))
+    x_prev = list(sy.symbols("xprev_0:8")); pe_prev = [sy.Symbol("Theta_1_prev")]
+    Pv = sy.Matrix(5, 5, lambda i, j: P_v[j * 5 + i])
+    vv = sy.Matrix(v)
+    stage = (vv.T * Pv * vv)[0, 0]
+    dx = sy.Matrix([a - b for a, b in zip(x, x_prev)])
+    arrival = 1e-4 * (dx.T * dx)[0, 0] + (T1 - pe_prev[0]) * P_p * (T1 - pe_prev[0])
+    inf = np.inf
+    return MHEDef(m, n_horizon=n_horizon, t_step=0.1, p_est=[T1], meas=list(phi) + list(u), stage_cost=stage, arrival_cost=arrival,
+                  v=v, x_prev=x_prev, p_est_prev=pe_prev, nl_cons_check_colloc_points=True,
+                  nl_cons=[NlCons("p_est_lb", -T1 + 1e-5, ub=0.0), NlCons("p_est_ub", T1 - 1e-3, ub=0.0)],
+                  x_lb=[-inf, -inf, -inf, -6, -6, -6, -inf, -inf], x_ub=[inf, inf, inf, 6, 6, 6, inf, inf],
+                  u_lb=[-5, -5], u_ub=[5, 5])

@@ -33,13 +33,15 @@ def build_hostsim(recipe, tag):
     for f in ("ipm_core.cuh", "ipm_solve.cuh", "ipm_refine.cuh", "ipm_sens.cuh", "dmb_host_util.h"):
         h.update((csrc / f).read_bytes())
     h.update((ROOT / "tests" / "hostsim" / "hostsim.cpp").read_bytes())
+    extra = os.environ.get("DMB_HOSTSIM_FLAGS", "").split()          # experiments only (e.g. -DDMB_EMU_FP32_PROJ)
+    h.update(" ".join(extra).encode())
     d = ROOT / "tests" / "hostsim" / "_build" / f"{tag}_{h.hexdigest()[:12]}"
     so = d / "hostsim.so"
     if not so.exists():
         d.mkdir(parents=True, exist_ok=True)
         (d / "problem_gen.h").write_text(src)
         tmp = d / f"hostsim.{os.getpid()}.tmp"
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-I{d}", f"-I{csrc}",
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", *extra, f"-I{d}", f"-I{csrc}",
                         str(ROOT / "tests" / "hostsim" / "hostsim.cpp"), "-o", str(tmp)], check=True)
         os.replace(tmp, so)                          # atomic: concurrent test processes may build the same emulation
     return ctypes.CDLL(str(so))
