@@ -10,6 +10,25 @@ from .sym.sx import (SX, DM, Function, vertcat, horzcat, veccat, vec, reshape, s
                      cosh, sign, floor, ceil, arctan, arcsin, arccos, fmin, fmax, atan2, arctan2, power)
 from .sym.struct import entry, struct_symSX, struct_SX, struct_symMX, struct_MX, SymStruct, NumStruct
 
+def vertsplit(x, incr=1):
+    """casadi.vertsplit: the rows of x in blocks of `incr` (list of DM / SX column blocks)."""
+    import numpy as _np
+    if isinstance(x, SX):
+        return [x[i:i + incr, :] for i in range(0, x.shape[0], incr)]
+    a = _np.asarray(x.full() if hasattr(x, "full") else x, dtype=float)
+    a = a.reshape(a.shape[0], -1)
+    return [DM(a[i:i + incr]) for i in range(0, a.shape[0], incr)]
+
+
+def horzsplit(x, incr=1):
+    import numpy as _np
+    if isinstance(x, SX):
+        return [x[:, i:i + incr] for i in range(0, x.shape[1], incr)]
+    a = _np.asarray(x.full() if hasattr(x, "full") else x, dtype=float)
+    a = a.reshape(a.shape[0], -1)
+    return [DM(a[:, i:i + incr]) for i in range(0, a.shape[1], incr)]
+
+
 MX = SX
 inf = float("inf")
 pi = 3.141592653589793

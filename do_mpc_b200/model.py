@@ -149,11 +149,12 @@ class Model:
     def __getitem__(self, ind):
         if not isinstance(ind, tuple):
             ind = (ind,)
+        # the structs themselves, like the reference (model/_model.py:164-191): `_x, _tvp = model['x', 'tvp']; _x['phi_2']`
         out = []
         for i in ind:
-            key = i if i.startswith("_") else "_" + i
-            if key == "_aux": key = "_aux_expression"
-            out.append(self._struct(key).cat if self.flags["setup"] else None)
+            name = i[1:] if i.startswith("_") else i
+            assert name in ("x", "u", "z", "p", "tvp", "y", "aux", "w", "v"), f"The queried variable {i} is not valid."
+            out.append(getattr(self, name))
         return out[0] if len(out) == 1 else out
 
     def _pre(self, vt):

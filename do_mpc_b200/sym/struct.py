@@ -271,6 +271,18 @@ class NumStruct(_StructBase):
         return _map_nested(self.layout.resolve(key), lambda idx: DM(self._v[np.atleast_1d(idx)].reshape(-1, 1)))
 
     def __setitem__(self, key, value):
+        if isinstance(value, (list, tuple)) and len(value) > 1:
+            # CasADi structure semantics: a list assigned to a slice over repeated entries goes item by item
+            # (`tvp_template['_tvp', :-1] = vertsplit(traj)`), each item broadcast over / matching its entry
+            leaves = _leaves(self.layout.resolve(key), [])
+            if len(leaves) == len(value):
+                for idx, item in zip(leaves, value):
+                    idx = np.atleast_1d(idx)
+                    a = np.asarray(item.full() if hasattr(item, "full") else item, dtype=float).ravel()
+                    if a.size not in (1, idx.size):
+                        raise ValueError(f"cannot assign {a.size} values to an entry of size {idx.size}")
+                    self._v[idx] = a if a.size > 1 else float(a[0])
+                return
         if isinstance(value, (DM, NumStruct)):
             value = value.full()
         elif isinstance(value, SX):

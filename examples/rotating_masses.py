@@ -71,3 +71,57 @@ def masses_mhe(model=None, setup=True):
     if setup:
         mhe.setup()
     return mhe
+
+
+def masses_mpc(model=None, setup=True):
+    """examples/rotating_oscillating_masses_mhe_mpc/template_mpc.py"""
+    from do_mpc_b200.casadi_api import DM, vertsplit
+    model = model or masses_model()
+    mpc = do_mpc.controller.MPC(model)
+    s = mpc.settings
+    s.n_robust, s.n_horizon, s.t_step, s.store_full_solution = 0, 20, 0.1, True
+    _x, _tvp = model["x", "tvp"]
+    mpc.set_objective(mterm=DM(1), lterm=(_x["phi_2"] - _tvp["phi_2_set"]) ** 2)
+    mpc.set_rterm(phi_m_set=1e-2)
+
+    def random_setpoint(tvp0):
+        tvp_next = (0.5 - np.random.rand()) * np.pi
+        switch = np.random.rand() >= 0.95
+        return (1 - switch) * tvp0 + switch * tvp_next
+    np.random.seed(999)
+    tvp_traj = [np.array([0])]
+    for i in range(400):
+        tvp_traj.append(random_setpoint(tvp_traj[i]))
+    tvp_traj = np.concatenate(tvp_traj)
+    tvp_template = mpc.get_tvp_template()
+
+    def tvp_fun(t_now):
+        ind = int(t_now / mpc.settings.t_step)
+        tvp_template["_tvp", :-1] = vertsplit(tvp_traj[ind:ind + mpc.settings.n_horizon])
+        return tvp_template
+    mpc.set_tvp_fun(tvp_fun)
+    mpc.set_uncertainty_values(Theta_1=2.25 * 1e-4 * np.array([1., 1.1]), Theta_2=2.25 * 1e-4 * np.array([1.]), Theta_3=2.25 * 1e-4 * np.array([1.]))
+    mpc.bounds["lower", "_u", "phi_m_set"] = -5
+    mpc.bounds["upper", "_u", "phi_m_set"] = 5
+    if setup:
+        mpc.setup()
+    return mpc
+
+
+def masses_simulator(model=None):
+    """examples/rotating_oscillating_masses_mhe_mpc/template_simulator.py"""
+    model = model or masses_model()
+    simulator = do_mpc.simulator.Simulator(model)
+    simulator.set_param(t_step=0.1)
+    p_template = simulator.get_p_template()
+
+    def p_fun(t_now):
+        p_template["Theta_1"] = 2.25e-4
+        p_template["Theta_2"] = 2.25e-4
+        p_template["Theta_3"] = 2.25e-4
+        return p_template
+    simulator.set_p_fun(p_fun)
+    tvp_template = simulator.get_tvp_template()
+    simulator.set_tvp_fun(lambda t_now: tvp_template)
+    simulator.setup()
+    return simulator

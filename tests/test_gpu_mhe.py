@@ -32,3 +32,27 @@ def test_mhe_five_steps_match_the_reference_run():
     assert d["_x"].shape == (5, 8) and d["_y"].shape == (5, 5) and d["_opt_x_num"].shape == (5, 423) and d["_lam_g_num"].shape == (5, 450)
     assert np.abs(d["_x"][1:] - g["x"][1:]).max() < 1e-5            # stored estimates = the reference's stored estimates
     assert mhe.S.launch_info()["n_launches"] >= 5
+
+
+def test_mpc_simulator_mhe_loop_like_the_reference_regression_test():
+    """testing/test_rotating_oscillating_masses_mhe_mpc.py end to end on the GPU: MPC -> simulator -> MHE, 5 steps, the stored
+    trajectories of all three modules against the reference's results_rotatingMasses.pkl (reference tolerance 1e-8 on its own
+    re-run; here the stated solver tolerance 1e-5 x scaling, simulator 1e-6)."""
+    import rotating_masses
+    g = np.load(GOLDEN / "loop_rotatingMasses.npz")
+    model = rotating_masses.masses_model()
+    mpc = rotating_masses.masses_mpc(model)
+    simulator = rotating_masses.masses_simulator(model)
+    mhe = rotating_masses.masses_mhe(model)
+    np.random.seed(99)
+    x0_true = np.random.rand(model.n_x) - 0.5
+    x0 = np.zeros(model.n_x)
+    mpc.x0 = x0; simulator.x0 = x0_true; mhe.x0 = x0; mhe.p_est0 = 1e-4
+    mpc.set_initial_guess(); mhe.set_initial_guess()
+    for k in range(5):
+        u0 = mpc.make_step(np.asarray(x0).reshape(-1, 1))
+        y_next = simulator.make_step(u0)
+        x0 = mhe.make_step(y_next)
+    assert np.abs(mpc.data["_u"] - g["mpc_u"]).max() < 1e-4 and np.abs(mpc.data["_x"] - g["mpc_x"]).max() < 1e-4
+    assert np.abs(simulator.data["_x"] - g["sim_x"]).max() < 1e-4 and np.abs(simulator.data["_u"] - g["sim_u"]).max() < 1e-4
+    assert np.abs(mhe.data["_x"] - g["mhe_x"]).max() < 1e-4 and np.abs(mhe.data["_y"] - g["mhe_y"]).max() < 1e-4
