@@ -70,3 +70,34 @@ def test_device_resident_closed_loop_equals_the_host_loop():
             x0 = sim.make_step(u0)
             assert np.abs((u0.ravel() - res["u"][k, b]) / r.u_scaling).max() < 1e-6, (b, k)
             assert np.abs((x0.ravel() - res["x"][k + 1, b]) / r.x_scaling).max() < 1e-7, (b, k)
+
+
+@pytest.mark.parametrize("name", ["oscillatingMasses_dae", "batch_reactor"])
+def test_device_closed_loop_with_algebraic_states_and_parameters(name):
+    """closed_loop_device for models with algebraic states (oscillating masses DAE) and parameters (batch reactor): the
+    device-resident loop reproduces the reference's golden closed-loop trajectories (VERDICT r1 #8)."""
+    from do_mpc_b200.rollout import closed_loop_device
+    make, _ = EXAMPLES[name]
+    mpc = make(setup=True)
+    mpc.S.set_options(max_iter=500)
+    model = mpc.model
+    g = golden(name)
+    sim = do_mpc.simulator.Simulator(model)
+    sim.set_param(t_step=mpc.settings.t_step)
+    if model.n_p:
+        p_num = sim.get_p_template()
+        for k, v in PLANT[name].items():
+            p_num[k] = v
+        sim.set_p_fun(lambda t: p_num)
+    sim.setup()
+    x0 = g["x"][0]
+    sim.x0 = x0.reshape(-1, 1)
+    if model.n_z:
+        sim.init_algebraic_variables()
+    B = 3
+    res = closed_loop_device(mpc, sim, np.tile(x0, (B, 1)), 4, U_prev=np.zeros((B, model.n_u)))
+    sx, su = mpc.recipe.x_scaling, mpc.recipe.u_scaling
+    assert np.all((res["status"] == 0) | (res["status"] == 1))
+    for b in range(B):
+        assert np.abs((res["x"][:5, b] - g["x"][:5]) / sx).max() < 1e-4 * max(1.0, np.abs(g["x"] / sx).max())
+        assert np.abs((res["u"][:4, b] - g["u"][:4]) / su).max() < 1e-4 * max(1.0, np.abs(g["u"] / su).max())
