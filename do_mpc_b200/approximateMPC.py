@@ -213,9 +213,15 @@ class AMPCSampler:
         rows = []
         steps = s.trajectory_length if s.closed_loop_flag else 1
         alive = np.ones(len(plan), bool)
+        t_start = np.array(self.mpc._t0, dtype=float).copy()
+        prev = None
         for k in range(steps):
             t0 = time.perf_counter()
-            out = self.mpc.make_step_batch(X, U)
+            # closed loop: the controller clock advances (time-varying parameters follow) and every step after the first starts
+            # from the previous solution, as mpc.make_step does in the reference's closed-loop sampler (_ampc_sampler.py:420-470)
+            self.mpc._t0 = t_start + k * self.mpc.settings.t_step
+            out = self.mpc.make_step_batch(X, U, return_full=s.closed_loop_flag, warm_from=prev)
+            prev = out if s.closed_loop_flag else None
             dt = (time.perf_counter() - t0) / len(plan)
             ok = np.asarray(out["success"], bool)
             for i in np.where(alive)[0]:
@@ -225,9 +231,11 @@ class AMPCSampler:
             if k + 1 < steps:
                 # the reference stops a trajectory at the first failed solve (_ampc_sampler.py:440-447)
                 alive &= ok
-                Xn = self.simulator.make_step_batch(X, out["u0"])[0]
+                Xn, _, sim_status = self.simulator.make_step_batch(X, out["u0"])
+                alive &= (np.asarray(sim_status) == 0)          # a failed integrator step ends the trajectory as well
                 U = np.where(alive[:, None], out["u0"], U)
                 X = np.where(alive[:, None], Xn, X)
+        self.mpc._t0 = t_start
         df = pd.DataFrame(rows)
         d = Path(s.data_dir) / s.dataset_name
         d.mkdir(parents=True, exist_ok=True)

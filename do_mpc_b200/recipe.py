@@ -95,7 +95,16 @@ def build_recipe(mpc) -> Recipe:
     n_eps, n_nl = mpc.n_eps, mpc.n_nl
     sx, su, sz = (np.asarray(v.full()).ravel() for v in (mpc._x_scaling.cat, mpc._u_scaling.cat, mpc._z_scaling.cat))
     if n_z and n_robust > 0:
+        # the reference evaluates lterm / nl_cons / aux of edge (k, s, b) with `_z[k, s, .]` of the stage-k scenario s although
+        # `_z[k, .]` is stored per CHILD scenario (_mpc.py:1213 vs :1233,1241,1252): for k < n_robust the edges of one node share
+        # the algebraic states of a sibling edge, which is not an edge-local structure
         raise NotImplementedError("algebraic states together with n_robust>0 (reference indexing quirk, SURVEY App. F.5)")
+    if n_robust > 0 and st.nl_cons_check_colloc_points and mpc.n_nl > 0:
+        # same quirk for the collocation states: the reference checks `_x[k+1, s, i]` of the stage-k scenario s (_mpc.py:1233)
+        raise NotImplementedError("nl_cons_check_colloc_points together with n_robust>0 (reference indexes the collocation states of the "
+                                  "stage-k scenario, SURVEY App. F.5)")
+    if np.any(np.asarray(mpc._p_scaling.cat.full()) != 1.0):
+        raise NotImplementedError("scaling of parameters (scaling['_p', ...]) is not applied by the generated stage functions")
 
     # ---- scaled stage symbols ----------------------------------------------------------------------------
     Xn = SX.sym("Xn", n_x); Un = SX.sym("Un", n_u); EPS = SX.sym("EPS", n_eps) if n_eps else SX.zeros(0, 1)
@@ -186,8 +195,11 @@ def build_recipe(mpc) -> Recipe:
     mterm = mpc.mterm_fun(XN * sxS, TV, PP)
     if mpc.flags["rterm_fun"]:
         rterm = mpc.rterm_fun(xu, uu, UPREV, SX.zeros(n_z, 1), TV, PP)   # u_prev enters scaled (reference :1265-1269)
-        if E.depends_on(rterm.ids()[0], Xn.ids()) :
+        if E.depends_on(rterm.ids()[0], Xn.ids()):
             raise NotImplementedError("user rterm depending on the states")
+        _zs = SX.sym("_rterm_z_probe", n_z) if n_z else None
+        if n_z and E.depends_on(mpc.rterm_fun(xu, uu, UPREV, _zs, TV, PP).ids()[0], _zs.ids()):
+            raise NotImplementedError("user rterm depending on the algebraic states")
     else:
         rf = np.asarray(mpc.rterm_factor.cat.full()).ravel()
         rterm = SX(0.0)
