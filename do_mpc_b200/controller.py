@@ -306,7 +306,7 @@ class MPC:
             entry("_x", repeat=[N + 1, S, 1 + P], struct=m._x),
             entry("_z", repeat=[N, S, Pz], struct=m._z),
             entry("_u", repeat=[N, S], struct=m._u),
-            entry("_eps", repeat=[N, S], struct=self._eps),
+            entry("_eps", repeat=[1 if st.nl_cons_single_slack else N, S], struct=self._eps),     # reference _mpc.py:1120-1133
         ])
         self._opt_p = SymStruct([
             entry("_x0", struct=m._x),
@@ -323,7 +323,7 @@ class MPC:
         self._update_bounds()
         self.nlp_cons_lb = np.zeros(r.n_g); self.nlp_cons_ub = np.zeros(r.n_g)
         for e in range(len(r.edge_k)):
-            o = r.edge_g_flat[e] + (r.n_z + r.n_x if r.discrete else r.n_y + r.n_x)
+            o = r.edge_g_flat[e] + (r.n_z + r.n_x - r.n_lift if r.discrete else r.n_y + r.n_x - 2 * r.n_lift)
             self.nlp_cons_lb[o:o + r.nl_rows_per_edge] = -np.inf
             self.nlp_cons_ub[o:o + r.nl_rows_per_edge] = r.nl_ub
         self._opt_x_num = self._opt_x(0.0)
@@ -475,7 +475,7 @@ class MPC:
             np.ascontiguousarray(np.asarray(U_prev, dtype=float).reshape(B, self.model.n_u))
         r = self.recipe
         P_ = np.zeros((B, r.n_p))
-        P_[:, r.p_x0:r.p_x0 + r.n_x] = X0
+        P_[:, r.p_x0:r.p_x0 + self.model.n_x] = X0
         P_[:, r.p_uprev:r.p_uprev + r.n_u] = U_prev
         if r.n_tvp:
             t = self.tvp_fun(self._t0)["_tvp"] if tvp is None else None
@@ -486,7 +486,10 @@ class MPC:
                 else np.asarray(p, dtype=float)
             P_[:, r.p_p:r.p_p + r.n_comb * r.n_pm] = pv.reshape(-1, r.n_comb * r.n_pm)
         Zs = None if not r.n_z else (np.tile(self._z0.full().ravel(), (B, 1)) if Z0 is None else np.asarray(Z0, dtype=float).reshape(B, r.n_z))
-        return P_, X0 / r.x_scaling, U_prev / r.u_scaling, None if Zs is None else Zs / r.z_scaling
+        x0s = X0 / r.x_scaling[:self.model.n_x]
+        if r.n_lift:                                   # lifted slack copies start at 0 like `_eps` after set_initial_guess()
+            x0s = np.concatenate([x0s, np.zeros((B, r.n_lift))], axis=1)
+        return P_, x0s, U_prev / r.u_scaling, None if Zs is None else Zs / r.z_scaling
 
     # ---- batched entry point ---------------------------------------------------------------------------------------------------------------------
     def make_step_batch(self, X0, U_prev=None, Z0=None, tvp=None, p=None, return_full=False, warm_from=None):

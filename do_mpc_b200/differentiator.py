@@ -78,6 +78,8 @@ class _SensNum:
 class DoMPCDifferentiator:
     def __init__(self, optimizer, **kwargs):
         assert optimizer.flags["setup"], "call setup() on the optimizer first"
+        if getattr(optimizer.recipe, "n_free0", 0):
+            raise NotImplementedError("sensitivities for problems with a free root state (MHE, nl_cons_single_slack)")
         self.optimizer = optimizer
         self.settings = NLPDifferentiatorSettings(**kwargs)
         self.status = NLPDifferentiatorStatus()

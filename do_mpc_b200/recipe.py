@@ -74,6 +74,7 @@ class Recipe:
     lam2flat: np.ndarray = None  # explicit internal multiplier row -> flat g row map (NLAM entries)
     w_init_from: np.ndarray = None   # initial value of an entry without flat counterpart: copy of another internal entry (-1: none)
     has_dummies: bool = None     # opt_x holds variables that appear nowhere (IPOPT's delta_w schedule is mimicked); None: MPC rule
+    n_lift: int = 0              # the last n_lift state components are a lifted global variable (nl_cons_single_slack), not model states
 
 
 def build_recipe(mpc) -> Recipe:
@@ -84,8 +85,10 @@ def build_recipe(mpc) -> Recipe:
     if st.open_loop and n_comb ** n_robust > 1:
         # with a single scenario the flag has no effect (one input sequence either way, reference _mpc.py:1113-1117)
         raise NotImplementedError("open_loop=True couples the inputs of all scenarios; not supported by the batched solver")
-    if st.nl_cons_single_slack and mpc.n_eps > 0:
-        raise NotImplementedError("nl_cons_single_slack couples all stages; not supported by the batched solver")
+    lift = bool(st.nl_cons_single_slack and mpc.n_eps > 0)
+    if lift and n_comb ** n_robust > 1:
+        # `_eps[0, s]` is shared by the nodes (k, s) of all stages (reference _mpc.py:1228-1254), which are not on one branch of the tree
+        raise NotImplementedError("nl_cons_single_slack together with a scenario tree (the shared slack couples different branches)")
     if m.n_w > 0:
         pass  # process noise symbols are fixed to zero in the controller (reference _mpc.py:1166)
     discrete = (m.model_type == "discrete")
@@ -93,6 +96,12 @@ def build_recipe(mpc) -> Recipe:
     P = 0 if discrete else (deg + 1) * ni
     Pz = max(P, 1)
     n_eps, n_nl = mpc.n_eps, mpc.n_nl
+    # nl_cons_single_slack: ONE slack vector for the whole horizon (reference _mpc.py:1120-1123).  It becomes n_l extra state
+    # components with the trivial dynamics eps+ = eps and a free root (the mechanism of the MHE's estimated parameters): every
+    # stage sees its own copy, the linear consistency rows keep the copies equal, only the root copy is bounded / mapped to opt_x.
+    n_l = n_eps if lift else 0
+    n_eps_flat = n_eps
+    if lift: n_eps = 0
     sx, su, sz = (np.asarray(v.full()).ravel() for v in (mpc._x_scaling.cat, mpc._u_scaling.cat, mpc._z_scaling.cat))
     if n_z and n_robust > 0:
         # the reference evaluates lterm / nl_cons / aux of edge (k, s, b) with `_z[k, s, .]` of the stage-k scenario s although
@@ -107,7 +116,9 @@ def build_recipe(mpc) -> Recipe:
         raise NotImplementedError("scaling of parameters (scaling['_p', ...]) is not applied by the generated stage functions")
 
     # ---- scaled stage symbols ----------------------------------------------------------------------------
-    Xn = SX.sym("Xn", n_x); Un = SX.sym("Un", n_u); EPS = SX.sym("EPS", n_eps) if n_eps else SX.zeros(0, 1)
+    Xa = SX.sym("Xn", n_x + n_l); Xn = Xa[0:n_x] if n_l else Xa
+    Un = SX.sym("Un", n_u); EPS = SX.sym("EPS", n_eps) if n_eps else SX.zeros(0, 1)
+    EPSv = Xa[n_x:n_x + n_l] if n_l else EPS          # the slack the stage functions see
     TV = SX.sym("TV", n_tvp) if n_tvp else SX.zeros(0, 1)
     PP = SX.sym("PP", n_pm) if n_pm else SX.zeros(0, 1)
     UPREV = SX.sym("UPREV", n_u)
@@ -123,7 +134,7 @@ def build_recipe(mpc) -> Recipe:
     # ---- edge unknowns and residuals gk (optimizer.py:891-993 / :820-824) ---------------------------------
     if discrete:
         n_y = n_z + n_x
-        Y = SX.sym("Y", n_y)
+        Ya = SX.sym("Y", n_y + n_l); Y = Ya
         zk = Y[0:n_z] if n_z else SX.zeros(0, 1)
         xf = Y[n_z:n_y]
         rows = []
@@ -136,7 +147,7 @@ def build_recipe(mpc) -> Recipe:
         yx_count, yz_count = 0, n_z
     else:
         n_y = P * (n_x + n_z)
-        Y = SX.sym("Y", n_y)
+        Ya = SX.sym("Y", n_y + n_l); Y = Ya
         _, C, D = collocation_constants(deg, st.collocation_type)
         C[np.abs(C) < 1e-14] = 0.0; D[np.abs(D) < 1e-14] = 0.0
         h = st.t_step / ni
@@ -176,23 +187,29 @@ def build_recipe(mpc) -> Recipe:
         xf_sel = np.arange((P - 1) * n_x, P * n_x)
         z_first = yz[0]; z_last = yz[P - 1]
     assert G.shape[0] == n_y
+    if n_l:
+        G = vertcat(G, EPSv - Ya[n_y:n_y + n_l])        # lifted slack: child copy = parent copy
+        xf_sel = np.concatenate([xf_sel, n_y + np.arange(n_l)])
+    n_ym = n_y; n_y = n_y + n_l
 
-    q = vertcat(Xn, Un, EPS, Y)
+    q = vertcat(Xa, Un, EPS, Ya)
     # ---- cost / constraints per edge (_mpc.py:1228-1275), evaluated on unscaled values ----------------------
     xu, uu = Xn * sxS, Un * suS
     lterm = mpc.lterm_fun(xu, uu, z_last * szS if n_z else z_last, TV, PP)
     epscost = mpc.epsterm_fun(EPS) if n_eps else SX(0.0)
+    if n_l:
+        lterm = lterm + mpc.epsterm_fun(EPSv)          # added once per edge like the reference does (_mpc.py:1254); one scenario: omega = 1
     nl_rows = []
     if n_nl:
         if st.nl_cons_check_colloc_points:
             for i in range(P):
-                nl_rows.append(mpc._nl_cons_fun(yx[i] * sxS, uu, yz[i] * szS if n_z else yz[i], TV, PP, EPS))
+                nl_rows.append(mpc._nl_cons_fun(yx[i] * sxS, uu, yz[i] * szS if n_z else yz[i], TV, PP, EPSv))
         else:
-            nl_rows.append(mpc._nl_cons_fun(xu, uu, z_first * szS if n_z else z_first, TV, PP, EPS))
+            nl_rows.append(mpc._nl_cons_fun(xu, uu, z_first * szS if n_z else z_first, TV, PP, EPSv))
     nl = vertcat(*nl_rows) if nl_rows else SX.zeros(0, 1)
     nl_ub = np.tile(np.asarray(mpc._nl_cons_ub.cat.full()).ravel(), len(nl_rows)) if nl_rows else np.zeros(0)
-    XN = SX.sym("XN", n_x)
-    mterm = mpc.mterm_fun(XN * sxS, TV, PP)
+    XN = SX.sym("XN", n_x + n_l)
+    mterm = mpc.mterm_fun((XN[0:n_x] if n_l else XN) * sxS, TV, PP)
     if mpc.flags["rterm_fun"]:
         rterm = mpc.rterm_fun(xu, uu, UPREV, SX.zeros(n_z, 1), TV, PP)   # u_prev enters scaled (reference :1265-1269)
         if E.depends_on(rterm.ids()[0], Xn.ids()):
@@ -242,7 +259,7 @@ def build_recipe(mpc) -> Recipe:
     sz_x = (N + 1) * S * (P + 1) * n_x
     o_z = o_x + sz_x; sz_zz = N * S * Pz * n_z
     o_u = o_z + sz_zz; sz_u = N * S * n_u
-    o_e = o_u + sz_u; sz_e = N * S * n_eps
+    o_e = o_u + sz_u; sz_e = (1 if lift else N) * S * n_eps_flat
     n_w = o_e + sz_e
     node_x_flat = np.array([o_x + ((node_k[n] * S + node_s[n]) * (P + 1) + P) * n_x for n in range(n_node)])
     node_u_flat = np.array([o_u + (node_k[n] * S + node_s[n]) * n_u if node_k[n] < N else -1 for n in range(n_node)])
@@ -255,7 +272,39 @@ def build_recipe(mpc) -> Recipe:
     if n_z: osc[o_z:o_z + sz_zz] = np.tile(sz, N * S * Pz)
     osc[o_u:o_u + sz_u] = np.tile(su, N * S)
 
+    extra = {}
+    if n_l:
+        # explicit internal <-> flat maps: node blocks (x, eps_copy, u), edge blocks (y of the model, eps_child)
+        w2f, init_from, nvp = [], [], n_x + n_l + n_u
+        for n in range(n_node):
+            w2f += [int(node_x_flat[n]) + i for i in range(n_x)] + ([o_e + i for i in range(n_l)] if n == 0 else [-1] * n_l)
+            w2f += [int(node_u_flat[n]) + i if node_u_flat[n] >= 0 else -1 for i in range(n_u)]
+            init_from += [-1] * n_x + ([-1] * n_l if n == 0 else [n_x + i for i in range(n_l)]) + [-1] * n_u
+        for e in range(n_edge):
+            if discrete:
+                w2f += [int(edge_yz_flat[e]) + i for i in range(n_z)] + [-1] * n_x
+            else:
+                w2f += [int(edge_yx_flat[e]) + i for i in range(P * n_x)] + [int(edge_yz_flat[e]) + i for i in range(P * n_z)]
+            w2f += [-1] * n_l
+            init_from += [-1] * n_ym + [n_x + i for i in range(n_l)]
+        l2f = list(range(n_x)) + [-1] * n_l
+        for e in range(n_edge):
+            g0 = int(egf[e])
+            if discrete:
+                l2f += [g0 + i for i in range(n_z)] + [-1] * n_x + [-1] * n_l
+                l2f += [g0 + n_z + i for i in range(n_x)] + [-1] * n_l
+                l2f += [g0 + n_z + n_x + i for i in range(nl_rows_per_edge)]
+            else:
+                l2f += [g0 + i for i in range(n_ym)] + [-1] * n_l
+                l2f += [g0 + n_ym + i for i in range(n_x)] + [-1] * n_l
+                l2f += [g0 + n_ym + n_x + i for i in range(nl_rows_per_edge)]
+        extra = dict(n_free0=n_l, w2flat=np.array(w2f), lam2flat=np.array(l2f), w_init_from=np.array(init_from), n_lift=n_l,
+                     has_dummies=bool(P > 0))
+        sx = np.concatenate([sx, np.ones(n_l)])
+    n_xm = n_x; n_x = n_x + n_l
+
     return Recipe(
+        **extra,
         n_x=n_x, n_u=n_u, n_z=n_z, n_tvp=n_tvp, n_pm=n_pm, n_comb=n_comb, n_eps=n_eps, n_nl=n_nl, N=N,
         n_robust=n_robust, P=P, Pz=Pz, discrete=discrete, n_y=n_y, nl_rows_per_edge=nl_rows_per_edge,
         n_branches=n_branches, n_scenarios=n_scen,
@@ -265,7 +314,7 @@ def build_recipe(mpc) -> Recipe:
         edge_omega=np.array(eom), n_w=n_w, n_g=g_row, n_p=n_p,
         node_x_flat=node_x_flat, node_u_flat=node_u_flat, node_eps_flat=node_eps_flat,
         edge_yx_flat=edge_yx_flat, edge_yz_flat=edge_yz_flat, edge_g_flat=np.array(egf),
-        p_x0=0, p_tvp=n_x, p_p=n_x + (N + 1) * n_tvp, p_uprev=n_x + (N + 1) * n_tvp + n_comb * n_pm,
+        p_x0=0, p_tvp=n_xm, p_p=n_xm + (N + 1) * n_tvp, p_uprev=n_xm + (N + 1) * n_tvp + n_comb * n_pm,
         q=q, tvp=TV, pp=PP, uprev=UPREV, xN=XN, G=G, lterm=lterm, epscost=epscost, nl=nl, nl_ub=nl_ub,
         rterm=rterm, mterm=mterm, aux=aux, xf_sel=xf_sel,
         x_scaling=sx, u_scaling=su, z_scaling=sz, opt_x_scaling=osc,

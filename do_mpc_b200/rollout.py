@@ -43,6 +43,8 @@ def closed_loop_device(mpc, simulator, X0, n_steps: int, U_prev=None, warm_start
         tvp_sim = torch.as_tensor(np.stack([simulator.tvp_fun(np.array([ts0 + k * dt])).full().ravel() for k in range(n_steps)]), dtype=f64, device=dev)
     if m.n_p:
         p_sim = torch.as_tensor(np.stack([simulator.p_fun(np.array([ts0 + k * dt])).full().ravel() for k in range(n_steps)]), dtype=f64, device=dev)
+    if r.n_lift:
+        raise NotImplementedError("closed_loop_device with nl_cons_single_slack")
     X0 = np.ascontiguousarray(np.asarray(X0, dtype=float).reshape(-1, r.n_x)); B = X0.shape[0]
     U0 = np.tile(mpc._u0.full().ravel(), (B, 1)) if U_prev is None else np.asarray(U_prev, dtype=float).reshape(B, r.n_u)
     x = torch.as_tensor(X0, dtype=f64, device=dev); up = torch.as_tensor(U0, dtype=f64, device=dev)

@@ -81,7 +81,7 @@ class HostSim:
             from do_mpc_b200.sym.struct import NumStruct
             for b in range(B):
                 s = self.mpc._opt_x(0.0)
-                s["_x"] = x0s[b]; s["_u"] = u0s[b]
+                s["_x"] = x0s[b][:r.n_x - r.n_lift]; s["_u"] = u0s[b]
                 if r.n_z: s["_z"] = z0s[b]
                 xg[b] = s.full().ravel()
             used = np.zeros(r.n_w, bool)
@@ -115,6 +115,8 @@ class HostSim:
 def cstr_batch_inputs(recipe, x0, u_prev):
     B = x0.shape[0]
     P = np.zeros((B, recipe.n_p))
-    P[:, recipe.p_x0:recipe.p_x0 + recipe.n_x] = x0
+    n_xm = recipe.n_x - recipe.n_lift
+    P[:, recipe.p_x0:recipe.p_x0 + n_xm] = x0
     P[:, recipe.p_uprev:recipe.p_uprev + recipe.n_u] = u_prev
-    return P, x0 / recipe.x_scaling, u_prev / recipe.u_scaling
+    x0s = np.concatenate([x0 / recipe.x_scaling[:n_xm], np.zeros((B, recipe.n_lift))], axis=1)
+    return P, x0s, u_prev / recipe.u_scaling

@@ -23,6 +23,7 @@ VARIANTS = {
     "terminal_bounds": dict(use_terminal_bounds=True),
     "hard_nl_cons_colloc": dict(nl_cons_check_colloc_points=True),
     "soft_nl_cons": dict(),
+    "soft_nl_cons_single_slack": dict(nl_cons_single_slack=True),     # one slack for the horizon: lifted to a state (recipe.py)
     "open_loop_single_scenario": dict(open_loop=True),        # no effect without a scenario tree (reference _mpc.py:1113-1117)
 }
 
@@ -38,13 +39,13 @@ def _build(name):
         mpc.terminal_bounds["upper", "C_b"] = 1.2          # reference form (_mpc.py:424-431)
     if name == "hard_nl_cons_colloc":
         mpc.set_nl_cons("T_K_hard", mpc.model.x["T_K"] - 0.5 * mpc.model.x["T_R"], ub=70.0)
-    if name == "soft_nl_cons":
+    if name.startswith("soft_nl_cons"):
         mpc.set_nl_cons("T_R_soft", mpc.model.x["T_R"], ub=132.0, soft_constraint=True, penalty_term_cons=50.0)
     mpc.prepare_nlp()
     d = dataclasses.replace(models.cstr_nominal(n_hor), **kw)
     if name == "hard_nl_cons_colloc":
         d = dataclasses.replace(d, nl_cons=[models.NlCons("T_K_hard", d.model.x[3] - 0.5 * d.model.x[2], ub=70.0)])
-    if name == "soft_nl_cons":
+    if name.startswith("soft_nl_cons"):
         d = dataclasses.replace(d, nl_cons=[models.NlCons("T_R_soft", d.model.x[2], ub=132.0, soft=True, penalty=50.0)])
     if name == "terminal_bounds":
         # only C_b gets a terminal upper bound: the other entries stay +inf (the default "terminal = state bounds" applies
@@ -71,6 +72,21 @@ def test_setting_variant_matches_oracle(name):
         ro = solve_mpc(nlp, d["x0"][i], d["u_prev"][i], solver=orc)
         assert bool(out["success"][b]) == ro["success"], (name, i, out["status"][b], ro["return_status"])
         if ro["success"]:
-            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= 1, (name, i)
-            assert np.abs(out["u0_scaled"][b] - ro["u0"] / r.u_scaling).max() < 1e-7, (name, i)
-            assert np.abs(out["x"][b] - ro["x"])[nlp.used_mask()].max() < 1e-6
+            # the lifted slack carries its own consistency multipliers: same solution, the path of the iterates differs slightly
+            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (4 if r.n_lift else 1), (name, i)
+            assert np.abs(out["u0_scaled"][b] - ro["u0"] / r.u_scaling).max() < (1e-5 if r.n_lift else 1e-7), (name, i)
+            used = nlp.used_mask()
+            if not r.n_lift:
+                assert np.abs(out["x"][b] - ro["x"])[used].max() < 1e-6
+            else:
+                # both are converged to tol = 1e-8 but along different iterates: compare through the KKT conditions of the flat
+                # (reference-layout) NLP at the returned x, lam_g, lam_x; weakly determined inputs may differ by more than u0 does
+                x, lam_g, lam_x = out["x"][b], out["lam_g"][b], out["lam_x"][b]
+                g = nlp.g(x, P[b])
+                eq = nlp.lbg == nlp.ubg
+                assert np.abs(g[eq]).max() < 1e-8 and np.all(g[~eq] <= nlp.ubg[~eq] + 1e-8)
+                stat = nlp.grad_f(x, P[b]) + nlp.jac_g(x, P[b]).T @ lam_g + lam_x
+                assert np.abs(stat[used]).max() < 1e-7, (name, i)
+                assert np.all(lam_g[~eq] >= -1e-9)
+                assert abs(out["f"][b] - ro["f"]) < 1e-7 * max(1.0, abs(ro["f"]))
+                assert np.abs(x - ro["x"])[used].max() < 1e-3
