@@ -103,11 +103,6 @@ def build_recipe(mpc) -> Recipe:
     n_eps_flat = n_eps
     if lift: n_eps = 0
     sx, su, sz = (np.asarray(v.full()).ravel() for v in (mpc._x_scaling.cat, mpc._u_scaling.cat, mpc._z_scaling.cat))
-    if n_z and n_robust > 0:
-        # the reference evaluates lterm / nl_cons / aux of edge (k, s, b) with `_z[k, s, .]` of the stage-k scenario s although
-        # `_z[k, .]` is stored per CHILD scenario (_mpc.py:1213 vs :1233,1241,1252): for k < n_robust the edges of one node share
-        # the algebraic states of a sibling edge, which is not an edge-local structure
-        raise NotImplementedError("algebraic states together with n_robust>0 (reference indexing quirk, SURVEY App. F.5)")
     if n_robust > 0 and st.nl_cons_check_colloc_points and mpc.n_nl > 0:
         # same quirk for the collocation states: the reference checks `_x[k+1, s, i]` of the stage-k scenario s (_mpc.py:1233)
         raise NotImplementedError("nl_cons_check_colloc_points together with n_robust>0 (reference indexes the collocation states of the "
@@ -224,6 +219,15 @@ def build_recipe(mpc) -> Recipe:
             if rf[i] != 0.0:
                 rterm = rterm + float(rf[i]) * (Un[i] - UPREV[i]) ** 2
     aux = m._aux_expression_fun(xu, uu, z_last * szS if n_z else z_last, TV, PP)
+    if n_z and n_comb ** n_robust > 1:
+        # the reference evaluates lterm / nl_cons / aux of edge (k, s, b) with `_z[k, s, .]` of the stage-k scenario s although
+        # `_z[k, .]` is stored per CHILD scenario (_mpc.py:1213 vs :1233,1241,1252): for k < n_robust the edges of one node would read
+        # the algebraic states of another edge.  Where none of the three depends on z the quirk has no effect and the tree is edge-local.
+        zids = list(zk.ids()) if discrete else [i_ for z_ in yz for i_ in z_.ids()]
+        for nm_, ex_ in (("lterm", lterm), ("nl_cons", nl), ("aux expressions", aux)):
+            if ex_.shape[0] and any(E.depends_on(i_, zids) for i_ in ex_.ids()):
+                raise NotImplementedError(f"{nm_} depending on algebraic states together with n_robust>0 "
+                                          "(reference indexing quirk, SURVEY App. F.5)")
 
     # ---- tree tables (optimizer.py:1011-1039) ----------------------------------------------------------------
     n_branches = [n_comb if k < n_robust else 1 for k in range(N)]

@@ -105,19 +105,22 @@ def oscillating_masses(n_horizon=7):
                   x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5])
 
 
-def oscillating_masses_dae(n_horizon=7):
+def oscillating_masses_dae(n_horizon=7, n_robust=0, uncertain=False):
     """examples/oscillating_masses_discrete_dae/template_model.py:33-75: the same plant written as a discrete DAE —
-    x+ = z, 0 = z - A x - B u (algebraic state z = x_next)."""
+    x+ = z, 0 = z - A x - B u (algebraic state z = x_next).  uncertain=True (test variant, not a reference example): the input
+    gain is scaled by an uncertain parameter kB so that the DAE can be put under a scenario tree."""
     x = list(sy.symbols("x0:4")); u = [sy.Symbol("u")]; z = list(sy.symbols("z0:4"))
+    kB = sy.Symbol("kB") if uncertain else 1
     A = np.array([[0.763, 0.460, 0.115, 0.020], [-0.899, 0.763, 0.420, 0.115],
                   [0.115, 0.020, 0.763, 0.460], [0.420, 0.115, -0.899, 0.763]])
     B = np.array([0.014, 0.063, 0.221, 0.367])
-    alg = [z[i] - sum(A[i, j] * x[j] for j in range(4)) - B[i] * u[0] for i in range(4)]
+    alg = [z[i] - sum(A[i, j] * x[j] for j in range(4)) - kB * B[i] * u[0] for i in range(4)]
     cost = sum(xi ** 2 for xi in x)
-    m = ModelDef("discrete", x=x, u=u, z=z, rhs=list(z), alg=alg, aux={"cost": cost})
+    m = ModelDef("discrete", x=x, u=u, z=z, p=[kB] if uncertain else [], rhs=list(z), alg=alg, aux={"cost": cost})
     mx = np.array([4.0, 10.0, 4.0, 10.0])
-    return MPCDef(m, n_horizon=n_horizon, t_step=0.5, n_robust=0, lterm=cost, mterm=cost, rterm_factor=[1e-4],
-                  x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5])
+    kw = dict(p_scenarios=_scenarios([1.0, 1.3, 0.7])) if uncertain else {}
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.5, n_robust=n_robust, lterm=cost, mterm=cost, rterm_factor=[1e-4],
+                  x_lb=-mx, x_ub=mx, u_lb=[-0.5], u_ub=[0.5], **kw)
 
 
 # ------------------------------------------------------------------------------------------------

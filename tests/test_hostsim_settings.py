@@ -90,3 +90,35 @@ def test_setting_variant_matches_oracle(name):
                 assert np.all(lam_g[~eq] >= -1e-9)
                 assert abs(out["f"][b] - ro["f"]) < 1e-7 * max(1.0, abs(ro["f"]))
                 assert np.abs(x - ro["x"])[used].max() < 1e-3
+
+
+def test_dae_under_a_scenario_tree_matches_oracle():
+    """Algebraic states together with n_robust > 0: supported where lterm / nl_cons / aux do not depend on z (the reference's
+    `_z[k, s]` indexing quirk, SURVEY App. F.5, has no effect then).  Discrete DAE with an uncertain input gain, 3 scenarios."""
+    import oscillating_masses as om
+    mpc = om.osc_dae_robust_mpc(n_horizon=5, n_robust=1, setup=False)
+    mpc.prepare_nlp()
+    nlp = FlatNLP(models.oscillating_masses_dae(5, n_robust=1, uncertain=True))
+    r = mpc.recipe
+    assert (r.n_w, r.n_g, r.n_p) == (nlp.n_w, nlp.n_g, nlp.n_p)
+    rng = np.random.default_rng(5)
+    X0 = rng.uniform(-1.0, 1.0, (3, 4)) * np.array([1.5, 3.0, 1.5, 3.0]); U0 = rng.uniform(-0.3, 0.3, (3, 1))
+    P, x0s, u0s, z0s = mpc.pack_batch(X0, U0, Z0=np.zeros((3, 4)))
+    sim = HostSim(mpc, "osc_dae_robust")
+    out = sim.solve(P, x0s, u0s, z0s)
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
+    for b in range(3):
+        ro = solve_mpc(nlp, X0[b], U0[b], z0=np.zeros(4), solver=orc)
+        assert np.array_equal(nlp.pack_p(X0[b], U0[b]), P[b])
+        assert bool(out["success"][b]) == ro["success"] == True
+        assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= 1
+        assert np.abs(out["u0_scaled"][b] - ro["u0"] / r.u_scaling).max() < 1e-7
+        assert np.abs(out["x"][b] - ro["x"])[nlp.used_mask()].max() < 1e-6
+
+
+def test_dae_tree_with_z_dependent_stage_cost_is_refused():
+    import oscillating_masses as om
+    mpc = om.osc_dae_robust_mpc(n_horizon=3, n_robust=1, setup=False)
+    mpc.set_objective(mterm=mpc.model.aux["cost"], lterm=mpc.model.aux["cost"] + mpc.model.z["x_next"][0] ** 2)
+    with pytest.raises(NotImplementedError):
+        mpc.prepare_nlp()
