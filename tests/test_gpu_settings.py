@@ -43,3 +43,23 @@ def test_soft_constraint_variants_on_gpu(name):
     assert np.abs(u.ravel() - out["u0"][0]).max() < 1e-6 * r.u_scaling.max()
     eps = mpc.opt_x_num["_eps", 0, 0].full().ravel()
     assert eps.shape == (1,) and eps[0] >= -1e-8
+
+
+def test_dae_under_a_scenario_tree_on_gpu():
+    import oscillating_masses as om
+    from oracle import models
+    from oracle.nlp import FlatNLP
+    mpc = om.osc_dae_robust_mpc(n_horizon=5, n_robust=1, setup=True)
+    nlp = FlatNLP(models.oscillating_masses_dae(5, n_robust=1, uncertain=True))
+    r = mpc.recipe
+    rng = np.random.default_rng(5)
+    X0 = rng.uniform(-1.0, 1.0, (32, 4)) * np.array([1.5, 3.0, 1.5, 3.0]); U0 = rng.uniform(-0.3, 0.3, (32, 1))
+    out = mpc.make_step_batch(X0, U0, Z0=np.zeros((32, 4)), return_full=True)
+    orc = IPMSolver(nlp, IpmOptions(max_iter=300))
+    for b in range(0, 32, 4):
+        ro = solve_mpc(nlp, X0[b], U0[b], z0=np.zeros(4), solver=orc)
+        assert bool(out["success"][b]) == ro["success"]
+        if ro["success"]:
+            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= 1
+            assert np.abs(out["u0"][b] - ro["u0"]).max() < 1e-7
+            assert np.abs(out["x"][b] - ro["x"])[nlp.used_mask()].max() < 1e-6
