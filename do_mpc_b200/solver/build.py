@@ -103,8 +103,10 @@ def launch_config(r: Recipe, src: str):
     return threads, ern_smem, vec_smem, min_ctas
 
 
-def build_library(r: Recipe, verbose: bool = False) -> Path:
-    src = generate(r)
+def build_library(r: Recipe, verbose: bool = False, src: str = None) -> Path:
+    """Generated problem library of a stage recipe (in-tree cache).  `src`: the already generated problem_gen.h (lets a caller
+    generate serially — the symbolic engine is not thread safe — and compile several libraries concurrently)."""
+    src = generate(r) if src is None else src
     threads, ern_smem, vec_smem, min_ctas = launch_config(r, src)
     extra = os.environ.get("DMB_EXTRA_NVCC_FLAGS", "").split()          # tuning experiments only
     key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{ern_smem}{vec_smem}{min_ctas}{extra}").encode()).hexdigest()[:16]
