@@ -133,6 +133,13 @@ enum DmbStatus {
 #define DMB_HAS_ARRIVAL 0
 #endif
 #define NXF (NX - DMB_NFREE0)
+// weight of an internal variable in the least-squares multiplier estimate (H := I): copies of a lifted global variable share
+// the unit weight of the flat NLP's single variable (codegen.py)
+#if DMB_HAS_INIT_FROM
+#define DMB_LSW(i) DMB_LS_WEIGHT[i]
+#else
+#define DMB_LSW(i) 1.0
+#endif
 
 // lane groups: one group factorises one edge
 #ifdef DMB_HOSTSIM
@@ -456,21 +463,26 @@ DMB_DEV double nl_ub_relaxed(const Inst& I, int e, int i) {
 // One thread per edge for the generated code; all threads for the reductions.
 // ---------------------------------------------------------------------------------------------------
 // per-thread partial sums of the barrier terms of a point: acc += -mu log(slack) (+ kappa_d mu slack for one-sided bounds),
-// bad = 1 outside the bounds
+// bad = 1 outside the bounds.  The logarithms of a thread's slacks are taken as ONE log of their running product (flushed
+// before it could leave the normal range): an FP64 log costs ~40 instructions, a multiplication one.
+#define DMB_LOGPROD(SLACK)                                                                                   \
+  do { prod *= (SLACK); if (prod < 1e-120 || prod > 1e120) { acc -= mu * log(prod); prod = 1.0; } } while (0)
 DMB_DEV void barrier_terms(const Ctx& c, const Inst& I, const double* w, const double* s, double mu, double kappa_d, double& acc, double& bad) {
+  double prod = 1.0;
   for (int i = c.tid; i < NWI; i += c.nthr) {
     const bool hl = I.lb[i] > -DMB_INF, hu = I.ub[i] < DMB_INF;
-    if (hl) { const double sl = w[i] - I.lb[i]; if (sl <= 0.0) bad = 1.0; else { acc -= mu * log(sl); if (!hu) acc += kappa_d * mu * sl; } }
-    if (hu) { const double su = I.ub[i] - w[i]; if (su <= 0.0) bad = 1.0; else { acc -= mu * log(su); if (!hl) acc += kappa_d * mu * su; } }
+    if (hl) { const double sl = w[i] - I.lb[i]; if (sl <= 0.0) bad = 1.0; else { DMB_LOGPROD(sl); if (!hu) acc += kappa_d * mu * sl; } }
+    if (hu) { const double su = I.ub[i] - w[i]; if (su <= 0.0) bad = 1.0; else { DMB_LOGPROD(su); if (!hl) acc += kappa_d * mu * su; } }
   }
 #if NNL > 0
   for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) {
     const double su = nl_ub_relaxed(I, i / NNL, i % NNL) - s[i];
-    if (su <= 0.0) bad = 1.0; else acc += -mu * log(su) + kappa_d * mu * su;
+    if (su <= 0.0) bad = 1.0; else { DMB_LOGPROD(su); acc += kappa_d * mu * su; }
   }
 #else
   (void)s;
 #endif
+  if (prod != 1.0) acc -= mu * log(prod);
 }
 
 // phi_out != nullptr (and phi_mu >= 0): also the barrier function phi_mu(w, s) = f + barrier terms, in the same reduction
@@ -667,7 +679,7 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
         const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
         double sig = 0.0, gb = 0.0;
         if (ls_mode) {
-          sig = 1.0;
+          sig = DMB_LSW(i);
           if (hl) gb -= I.zL[i];
           if (hu) gb += I.zU[i];
         } else if (I.resto) resto_terms(I.zeta, mu, wy, I.go[i], lo, hi, hl, hu, sig, gb);
@@ -1035,7 +1047,7 @@ DMB_PHASE void riccati_backward_t(const Ctx& c, const Inst& I, double mu, double
       const bool hl = lo > -DMB_INF, hu = hi < DMB_INF;
       double sig = delta, gb = 0.0;
       if (ls_mode) {
-        sig = 1.0;
+        sig = DMB_LSW(gi);
         if (hl) gb -= I.zL[gi];
         if (hu) gb += I.zU[gi];
       } else if (I.resto) { resto_terms(I.zeta, mu, wx, I.go[gi], lo, hi, hl, hu, sig, gb); sig += delta; }

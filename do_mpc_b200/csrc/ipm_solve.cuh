@@ -199,7 +199,15 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
       // ---- gradient based scaling at the user's starting point (before the bound push) ----------------------------
       {
         double g = 0.0;
-        for (int i = c.tid; i < NWI; i += c.nthr) g = fmax(g, fabs(I.go[i]));
+        for (int i = c.tid; i < NWI; i += c.nthr) {
+          double gi = I.go[i];
+#if DMB_HAS_INIT_FROM
+          // the objective gradient w.r.t. a lifted global variable is the sum over its copies (what the flat NLP's scaling sees)
+          if (DMB_W_INIT_FROM[i] >= 0) gi = 0.0;
+          else if (DMB_LS_WEIGHT[i] < 1.0) for (int j = 0; j < NWI; ++j) if (DMB_W_INIT_FROM[j] == i) gi += I.go[j];
+#endif
+          g = fmax(g, fabs(gi));
+        }
         g = block_max(c, g, red);
         if (g > o.nlp_scaling_max_gradient) I.df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
       }
@@ -243,6 +251,12 @@ DMB_DEV void solve_instance(const Ctx& c, const Inst& I_in, const DmbOptions& o,
         I.zL[i] = hl ? zl : 0.0;
         I.zU[i] = hu ? zu : 0.0;
       }
+#if DMB_HAS_INIT_FROM
+      // copies of a lifted global variable follow the pushed root copy: the linear consistency rows hold at the starting point, so
+      // all copies take the same Newton steps as the single variable of the flat NLP
+      CTA_SYNC();
+      for (int i = c.tid; i < NWI; i += c.nthr) if (DMB_W_INIT_FROM[i] >= 0) I.w[i] = I.w[DMB_W_INIT_FROM[i]];
+#endif
       if (ws) {
         for (int i = c.tid; i < NLAM; i += c.nthr) {
           const int fl = DMB_LAM2FLAT[i];

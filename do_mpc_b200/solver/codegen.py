@@ -307,6 +307,15 @@ def generate(r: Recipe) -> str:
         assert len(l2f) == r.n_x + n_edge * (r.n_y + r.n_x + n_nl), (len(l2f), r.n_x + n_edge * (r.n_y + r.n_x + n_nl))
     assert len(w2f) == n_node * n_vp + n_edge * r.n_y, (len(w2f), n_node * n_vp + n_edge * r.n_y)
     init_from = [-1] * len(w2f) if r.w_init_from is None else [int(v) for v in r.w_init_from]
+    # least-squares multiplier estimate: the copies of a lifted global variable share the unit weight of the single variable of
+    # the flat NLP (weight 1/#copies each), which makes the estimate of the reference multipliers identical to the flat one
+    grp = {}
+    for i_, v in enumerate(init_from):
+        if v >= 0: grp.setdefault(v, []).append(i_)
+    lsw = [1.0] * len(w2f)
+    for root_, members in grp.items():
+        for i_ in [root_] + members: lsw[i_] = 1.0 / (1 + len(members))
+    H.append(_ctab("double", "DMB_LS_WEIGHT", [_dbl(v) for v in lsw] if grp else [_dbl(1.0)]))
     H.append(f"#define DMB_HAS_INIT_FROM {int(any(v >= 0 for v in init_from))}")
     H.append(_ctab("int", "DMB_W_INIT_FROM", init_from if any(v >= 0 for v in init_from) else [0]))
     H.append("#define DMB_W2FLAT_INIT {" + ", ".join(str(v) for v in w2f) + "}")

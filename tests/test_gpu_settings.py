@@ -29,10 +29,12 @@ def test_soft_constraint_variants_on_gpu(name):
         if not ro["success"]:
             continue
         assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (4 if r.n_lift else 1), (name, i)
-        assert np.abs(out["u0"][b] - ro["u0"]).max() < 1e-5 * r.u_scaling.max(), (name, i)
+        # lifted slack: the inertia regularisation delta_w acts on every copy, so the iterates are not the flat NLP's; both end at
+        # KKT points to tol = 1e-8 and the weakly determined cooling input agrees to 2e-4 of its scale (flat NLP: 1e-7)
+        assert (np.abs(out["u0"][b] - ro["u0"]) / r.u_scaling).max() < (2e-4 if r.n_lift else 1e-7), (name, i)
         x, lam_g, lam_x, p = out["x"][b], out["lam_g"][b], out["lam_x"][b], out["p"][b]
         g = nlp.g(x, p)
-        assert np.abs(g[eq]).max() < 1e-8 and np.all(g[~eq] <= nlp.ubg[~eq] + 1e-8)
+        assert np.abs(g[eq]).max() < 1e-8 and np.all(g[~eq] <= nlp.ubg[~eq] + 2e-8 * np.maximum(1.0, np.abs(nlp.ubg[~eq])))   # bound_relax_factor 1e-8 (relative)
         stat = nlp.grad_f(x, p) + nlp.jac_g(x, p).T @ lam_g + lam_x
         assert np.abs(stat[used]).max() < 1e-7, (name, i)
         assert abs(out["f"][b] - ro["f"]) < 1e-7 * max(1.0, abs(ro["f"]))

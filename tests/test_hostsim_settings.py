@@ -84,7 +84,7 @@ def test_setting_variant_matches_oracle(name):
                 x, lam_g, lam_x = out["x"][b], out["lam_g"][b], out["lam_x"][b]
                 g = nlp.g(x, P[b])
                 eq = nlp.lbg == nlp.ubg
-                assert np.abs(g[eq]).max() < 1e-8 and np.all(g[~eq] <= nlp.ubg[~eq] + 1e-8)
+                assert np.abs(g[eq]).max() < 1e-8 and np.all(g[~eq] <= nlp.ubg[~eq] + 2e-8 * np.maximum(1.0, np.abs(nlp.ubg[~eq])))   # bound_relax_factor 1e-8 (relative)
                 stat = nlp.grad_f(x, P[b]) + nlp.jac_g(x, P[b]).T @ lam_g + lam_x
                 assert np.abs(stat[used]).max() < 1e-7, (name, i)
                 assert np.all(lam_g[~eq] >= -1e-9)

@@ -74,6 +74,7 @@ def test_kernel_source_on_the_mhe_recipe(nlp, gold):
         ro = orc.solve(x_init, gold["opt_p_num"][t])
         # the lifted formulation carries multipliers for the parameter-consistency rows: the least-squares multiplier estimate
         # and the dual scaling s_d differ slightly from the flat NLP's, so iteration counts agree only approximately
+        print("MHE step", t, "iterations kernel", int(out["iter_count"][0]), "oracle", ro["iter_count"])
         assert abs(int(out["iter_count"][0]) - ro["iter_count"]) <= 3, (t, out["iter_count"], ro["iter_count"])
         # multipliers in the reference's g layout (lifted-parameter rows have no flat counterpart)
         lam = mhe.reference_multipliers(out["x"][0], out["lam_g"][0], gold["opt_p_num"][t])
