@@ -744,12 +744,27 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
       for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
       // ---- back substitution, one lane per right-hand side; then Yext = [-X | x_rhs] --------------------------------
       for (int j = c.gl; j < NE; j += GSZ) {
+#if NY <= 16
+        // the lane's solution column stays in registers (fully unrolled: static indices); same operation order as the loop below
+        double xv[NY];
+#pragma unroll
+        for (int k = NY - 1; k >= 0; --k) {
+          double x = T[k * TILE_LD + NY + j];
+#pragma unroll
+          for (int cc = k + 1; cc < NY; ++cc) x -= T[k * TILE_LD + cc] * xv[cc];
+          xv[k] = x * T[STG_INVD + k];
+        }
+        const double sgn = j < NVP ? -1.0 : 1.0;
+#pragma unroll
+        for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = sgn * xv[k];
+#else
         for (int k = NY - 1; k >= 0; --k) {
           double x = T[k * TILE_LD + NY + j];
           for (int cc = k + 1; cc < NY; ++cc) x -= T[k * TILE_LD + cc] * T[cc * TILE_LD + NY + j];
           T[k * TILE_LD + NY + j] = x * T[STG_INVD + k];
         }
         if (j < NVP) for (int k = 0; k < NY; ++k) T[k * TILE_LD + NY + j] = -T[k * TILE_LD + NY + j];
+#endif
       }
     }
     WARP_SYNC();
@@ -1570,6 +1585,29 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     }
     WARP_SYNC();
     // ---- G_y' lam = r with P G_y = L U (diagonal of U stored as reciprocal):  U' a = r ; L' b = a ; lam = P' b ----------
+#if !defined(DMB_HOSTSIM) && (NY <= GSZ)
+    {
+      // lane r of the group carries entry r of the vector; the pivot entry travels by shuffle: no barriers, no shared-memory
+      // round trips (same operations in the same order as the loop version below)
+      const unsigned gmask = GSZ == 32 ? DMB_FULL : (0xffffu << (c.lane & 16));
+      const int gbase = c.lane & ~(GSZ - 1);
+      const bool mine = act && c.gl < NY;
+      double rr = mine ? rv[c.gl] : 0.0;
+#pragma unroll
+      for (int k = 0; k < NY; ++k) {
+        const double ak = __shfl_sync(gmask, rr, gbase + k) * T[k * TILE_LD + k];
+        if (mine && c.gl > k) rr -= T[k * TILE_LD + c.gl] * ak;
+        if (c.gl == k) rr = ak;
+      }
+#pragma unroll
+      for (int k = NY - 1; k >= 0; --k) {
+        const double bk = __shfl_sync(gmask, rr, gbase + k);
+        if (mine && c.gl < k) rr -= T[k * TILE_LD + c.gl] * bk;
+      }
+      if (mine) I.lamn[LAM_EDGE(e) + (int)eb[EB_PIV + c.gl]] = rr;                                       // lam = P' b
+    }
+    WARP_SYNC();
+#else
     for (int k = 0; k < NY; ++k) {
       double ak = 0.0;
       if (act) {
@@ -1586,6 +1624,7 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     }
     if (act) for (int j = c.gl; j < NY; j += GSZ) I.lamn[LAM_EDGE(e) + (int)eb[EB_PIV + j]] = rv[j];      // lam = P' b
     WARP_SYNC();
+#endif
   }
   CTA_SYNC();
 }
