@@ -107,8 +107,6 @@ def build_recipe(mpc) -> Recipe:
         # same quirk for the collocation states: the reference checks `_x[k+1, s, i]` of the stage-k scenario s (_mpc.py:1233)
         raise NotImplementedError("nl_cons_check_colloc_points together with n_robust>0 (reference indexes the collocation states of the "
                                   "stage-k scenario, SURVEY App. F.5)")
-    if np.any(np.asarray(mpc._p_scaling.cat.full()) != 1.0):
-        raise NotImplementedError("scaling of parameters (scaling['_p', ...]) is not applied by the generated stage functions")
 
     # ---- scaled stage symbols ----------------------------------------------------------------------------
     Xa = SX.sym("Xn", n_x + n_l); Xn = Xa[0:n_x] if n_l else Xa
@@ -120,11 +118,15 @@ def build_recipe(mpc) -> Recipe:
     W0 = SX.zeros(m.n_w, 1)
     sxS, suS, szS = SX(sx.reshape(-1, 1)), SX(su.reshape(-1, 1)), SX(sz.reshape(-1, 1)) if n_z else SX.zeros(0, 1)
 
+    # scaling['_p', ...] multiplies the parameters seen by the model equations only (optimizer.py:811-815); cost and constraints get opt_p['_p']
+    sp = np.asarray(mpc._p_scaling.cat.full()).ravel() if n_pm else np.zeros(0)
+    PPm = PP * SX(sp.reshape(-1, 1)) if n_pm and np.any(sp != 1.0) else PP
+
     def rhs_scaled(x, u, z):          # optimizer.py:807-818
-        return m._rhs_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PP, W0) / sxS
+        return m._rhs_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PPm, W0) / sxS
 
     def alg(x, u, z):
-        return m._alg_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PP, W0)
+        return m._alg_fun(x * sxS, u * suS, z * szS if n_z else z, TV, PPm, W0)
 
     # ---- edge unknowns and residuals gk (optimizer.py:891-993 / :820-824) ---------------------------------
     if discrete:

@@ -122,3 +122,23 @@ def test_dae_tree_with_z_dependent_stage_cost_is_refused():
     mpc.set_objective(mterm=mpc.model.aux["cost"], lterm=mpc.model.aux["cost"] + mpc.model.z["x_next"][0] ** 2)
     with pytest.raises(NotImplementedError):
         mpc.prepare_nlp()
+
+
+def test_parameter_scaling_reaches_the_model_equations_only():
+    """scaling['_p', name] multiplies the parameter inside rhs / alg (reference optimizer.py:811-815): a controller with
+    scaling 2 and uncertainty values v / 2 solves the same NLP as the unscaled controller with values v."""
+    import cstr
+    ref = cstr.cstr_robust_mpc(n_horizon=4, n_robust=1, setup=False); ref.prepare_nlp()
+    mpc = cstr.cstr_robust_mpc(n_horizon=4, n_robust=1, setup=False)
+    mpc.scaling["_p", "alpha"] = 2.0; mpc.scaling["_p", "beta"] = 0.5
+    mpc.set_uncertainty_values(alpha=np.array([1.0, 1.05, 0.95]) / 2.0, beta=np.array([1.0, 1.1, 0.9]) / 0.5)
+    mpc.prepare_nlp()
+    d = np.load(GOLDEN / "cstr_dataset.npz")
+    idx = np.where(d["success"])[0][[0, 3]]
+    outs = []
+    for m_, tag in ((ref, "cstr_rob4"), (mpc, "cstr_rob4_pscaled")):
+        P, x0s, u0s, _ = m_.pack_batch(d["x0"][idx], d["u_prev"][idx])
+        outs.append(HostSim(m_, tag).solve(P, x0s, u0s))
+    assert np.array_equal(outs[0]["status"], outs[1]["status"]) and (outs[0]["status"] == 0).all()
+    assert np.array_equal(outs[0]["iter_count"], outs[1]["iter_count"])
+    assert np.abs(outs[0]["x"] - outs[1]["x"]).max() < 1e-9
