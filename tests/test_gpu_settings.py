@@ -28,7 +28,7 @@ def test_soft_constraint_variants_on_gpu(name):
         assert bool(out["success"][b]) == ro["success"], (name, i)
         if not ro["success"]:
             continue
-        assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (4 if r.n_lift else 1), (name, i)
+        assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (6 if r.n_lift else 1), (name, i)
         # lifted slack: the inertia regularisation delta_w acts on every copy, so the iterates are not the flat NLP's; both end at
         # KKT points to tol = 1e-8 and the weakly determined cooling input agrees to 2e-4 of its scale (flat NLP: 1e-7)
         assert (np.abs(out["u0"][b] - ro["u0"]) / r.u_scaling).max() < (2e-4 if r.n_lift else 1e-7), (name, i)

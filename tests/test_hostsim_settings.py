@@ -73,7 +73,7 @@ def test_setting_variant_matches_oracle(name):
         assert bool(out["success"][b]) == ro["success"], (name, i, out["status"][b], ro["return_status"])
         if ro["success"]:
             # the lifted slack carries its own consistency multipliers: same solution, the path of the iterates differs slightly
-            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (4 if r.n_lift else 1), (name, i)
+            assert abs(int(out["iter_count"][b]) - ro["iter_count"]) <= (6 if r.n_lift else 1), (name, i)
             assert np.abs(out["u0_scaled"][b] - ro["u0"] / r.u_scaling).max() < (1e-5 if r.n_lift else 1e-7), (name, i)
             used = nlp.used_mask()
             if not r.n_lift:
