@@ -887,6 +887,19 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
 #define DMB_PACC double
 #define DMB_PMUL(x, y) ((x) * (y))
 #endif
+#if !defined(DMB_EMU_FP32_PROJ)
+      // one lane per column of Yext: the column in registers, the sparse rows as generated straight-line code (gen_hy_products)
+      for (int a = c.gl; a < NE; a += GSZ) {
+        double yc[NY], mc[NY], nc[NVP];
+#pragma unroll
+        for (int j = 0; j < NY; ++j) yc[j] = T[j * TILE_LD + NY + a];
+        gen_hy_products(T + STG_HNZ, T + STG_SIGY, yc, mc, nc);
+#pragma unroll
+        for (int j = 0; j < NY; ++j) T[j * TILE_LD + TILE_M + a] = mc[j];
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) T[STG_N + i * NE + a] = nc[i];
+      }
+#else
       for (int idx = c.gl; idx < NQ * NE; idx += GSZ) {
         const int rq = idx / NE, a = idx - rq * NE;            // rq < NVP: N row, else M row
         DMB_PACC s = 0.0;
@@ -899,6 +912,7 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
           T[(rq - NVP) * TILE_LD + TILE_M + a] = s;
         } else T[STG_N + rq * NE + a] = s;
       }
+#endif
     }
     WARP_SYNC();
     SUB_TICK(I, 3);
@@ -1398,6 +1412,28 @@ DMB_DEV void load_tile_image(const Ctx& c, const Inst& I, const double* eb, doub
 #endif
 }
 
+// recovery phase, data of one edge that does not depend on the roll-out: the [LU | Yext] tile image (one TMA bulk copy, tracked by
+// the group's mbarrier) and the sparse blocks, staged into the group's tile
+DMB_DEV void fr_stage_edge(const Ctx& c, const Inst& I, const double* res, int ls_mode, int refine, int gy_off, int e, bool act, double* T) {
+  const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
+#if DMB_TMA
+  if (act && c.gl == 0) tma_load_1d(T, eb + EB_IMG, IMG_SZ * 8, I.mbar + c.grp);       // one bulk copy in flight per lane group
+#endif
+  if (act) {
+    // coalesced, independent loads while the image lands
+    DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
+    DMB_COPY_BATCH(NY, c.gl, GSZ, eb[gy_off + idx], T[STG_GY + idx] = val);
+    DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
+#if NNL > 0
+    for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
+    // re-solve with a new right-hand side: r_d = Sigma_s rp_d (zero in a refinement solve, where the condensed rows are exact)
+    for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? eb[EB_SIGS + i] * res[LAM_EDGE(e) + NY + NX + i] : eb[EB_RD + i]; }
+#else
+    (void)res; (void)refine;
+#endif
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward roll-out (warp 0) then, per edge by its lane group: dy = Yext [dv; 1], new multipliers by a
 // transposed LU solve in the group tile, inequality steps.
@@ -1406,6 +1442,12 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
   const int gy_off = refine ? EB_GY2 : EB_GY;
   SUB_START();
   const bool par = DMB_TREE_PAR && c.nwarp > 1;     // scenario trees: the nodes of a stage roll out on different warps
+  // chains: warp 0 rolls out alone — the other warps fetch the data of their first edges meanwhile (the tiles are idle here)
+  const bool early = !par && c.nwarp > 1;
+  if (early && c.warp != 0) {
+    const int e = c.grp;
+    fr_stage_edge(c, I, res, ls_mode, refine, gy_off, e, e < NEDGE, tile_base + (size_t)c.grp * TILE_SZ);
+  }
   {
 #if DMB_NSCEN == 1 && !defined(DMB_HOSTSIM) && (NXI <= 8) && (NVP <= 8) && !defined(DMB_NO_CHAIN_ROLLOUT)
     // chains: the state step d xi travels in registers (lane t owns d xi_t), broadcast by shuffles; nothing on the dependent
@@ -1512,19 +1554,8 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
     const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
-#if DMB_TMA
-    if (act && c.gl == 0) tma_load_1d(T, eb + EB_IMG, IMG_SZ * 8, I.mbar + c.grp);       // [LU | Yext] image: one bulk copy in flight
-#endif
+    if (!(early && e0 == 0 && c.warp != 0)) fr_stage_edge(c, I, res, ls_mode, refine, gy_off, e, act, T);
     if (act) {
-      // stage the sparse data of this edge (coalesced, independent loads) while the image lands
-      DMB_COPY_BATCH(DMB_NNZ_H, c.gl, GSZ, eb[EB_HNZ + idx], T[STG_HNZ + idx] = ls_mode ? 0.0 : val);
-      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[gy_off + idx], T[STG_GY + idx] = val);
-      DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
-#if NNL > 0
-      for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
-      // re-solve with a new right-hand side: r_d = Sigma_s rp_d (zero in a refinement solve, where the condensed rows are exact)
-      for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? eb[EB_SIGS + i] * res[LAM_EDGE(e) + NY + NX + i] : eb[EB_RD + i]; }
-#endif
       const double* dvp = I.dw + NODE_OFF(EDGE_PARENT_OF(e));
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];
       // continuity multiplier = gradient of the child's cost-to-go

@@ -131,6 +131,18 @@ def generate(r: Recipe) -> str:
         for c_, k in sorted(row):
             hr_col.append(c_); hr_idx.append(k)
         hr_start.append(len(hr_col))
+    # straight-line products of one column of Yext with the sparse Hessian rows (factor phase, n_y <= 16): mc = (H_yy + Sigma_y) yc,
+    # nc = H_vy yc; same summation order as the CSR loops they replace (row entries by ascending column, Sigma term last)
+    body = []
+    for rq in range(n_q):
+        terms = [f"hnz[{hr_idx[t]}] * yc[{hr_col[t] - n_vp}]" for t in range(hr_start[rq], hr_start[rq + 1]) if hr_col[t] >= n_vp]
+        if rq >= n_vp:
+            j = rq - n_vp
+            body.append(f"  {{ double s = 0.0; " + " ".join(f"s += {t_};" for t_ in terms) + f" s += sigy[{j}] * yc[{j}]; mc[{j}] = s; }}")
+        else:
+            body.append(f"  {{ double s = 0.0; " + " ".join(f"s += {t_};" for t_ in terms) + f" nc[{rq}] = s; }}")
+    out.append(_fn("gen_hy_products", "const double* __restrict__ hnz, const double* __restrict__ sigy, const double* __restrict__ yc, "
+                   "double* __restrict__ mc, double* __restrict__ nc", "  (void)hnz; (void)sigy; (void)yc; (void)mc; (void)nc;\n" + "\n".join(body)))
     # column-wise (CSC) view of the Jacobian nonzeros: J' lam products with one lane per column
     jcols = [[] for _ in range(n_q)]
     for k, c_ in enumerate(jc):
