@@ -59,9 +59,15 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
   DmbShared* S = reinterpret_cast<DmbShared*>(sm + SM_DOUBLES);
   __shared__ int cur;
   __shared__ DmbResult result;
-  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
-        (int)(threadIdx.x % GSZ), (int)(threadIdx.x / GSZ), (int)(blockDim.x / GSZ)};
-  double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
+  // the block size is the compile-time DMB_THREADS (dmb_launch); the thread index is read ONCE: under register pressure the
+  // compiler otherwise re-reads %tid.x (S2R, ~6 % of the stall samples in the r2y profile) wherever c.tid / c.lane / c.gl is used
+  unsigned tid_;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
+  Ctx c{(int)tid_, (int)DMB_THREADS, (int)(tid_ & 31), (int)(tid_ >> 5), (int)(DMB_THREADS >> 5),
+        (int)(tid_ % GSZ), (int)(tid_ / GSZ), (int)(DMB_THREADS / GSZ)};
+  unsigned bid_;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid_));
+  double* slot = a.ws + (size_t)bid_ * SLOT_DOUBLES;
   Inst I;
   bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot + SLOT_VEC);
   I.er = DMB_ERN_SMEM ? sm + SM_ER : slot + SLOT_ERN;
@@ -70,13 +76,13 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.o.bound_relax_factor; I.relax_max = a.o.constr_viol_tol;
   I.mbar = S->mbar; I.mphase = S->mphase;
-  if (threadIdx.x == 0) {
+  if (c.tid == 0) {
     for (int i = 0; i < DMB_NGRP; ++i) { mbar_init(S->mbar + i, 1); S->mphase[i] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   while (true) {
-    if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
+    if (c.tid == 0) cur = atomicAdd(a.counter, 1);
     __syncthreads();
     const int b = cur;
     __syncthreads();
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_solve_kernel(co
     store_solution(c, I, df, a.x ? a.x + (size_t)b * DMB_NW : nullptr, a.lam_g ? a.lam_g + (size_t)b * DMB_NG : nullptr,
                    a.lam_x ? a.lam_x + (size_t)b * DMB_NW : nullptr, a.g ? a.g + (size_t)b * DMB_NG : nullptr);
     for (int i = c.tid; i < NU; i += c.nthr) a.u0[(size_t)b * NU + i] = I.w[NODE_OFF(0) + NX + i];
-    if (threadIdx.x == 0) {
+    if (c.tid == 0) {
       a.f[b] = result.f; a.status[b] = result.status; a.iters[b] = result.iters;
       if (a.stats) {
         a.stats[(size_t)b * DMB_NSTAT + DMB_STAT_MU] = result.mu;
@@ -128,9 +134,15 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_sens_kernel(con
   double* sm = reinterpret_cast<double*>(smem_raw);
   DmbShared* S = reinterpret_cast<DmbShared*>(sm + SM_DOUBLES);
   __shared__ int cur;
-  Ctx c{(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
-        (int)(threadIdx.x % GSZ), (int)(threadIdx.x / GSZ), (int)(blockDim.x / GSZ)};
-  double* slot = a.ws + (size_t)blockIdx.x * SLOT_DOUBLES;
+  // the block size is the compile-time DMB_THREADS (dmb_launch); the thread index is read ONCE: under register pressure the
+  // compiler otherwise re-reads %tid.x (S2R, ~6 % of the stall samples in the r2y profile) wherever c.tid / c.lane / c.gl is used
+  unsigned tid_;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
+  Ctx c{(int)tid_, (int)DMB_THREADS, (int)(tid_ & 31), (int)(tid_ >> 5), (int)(DMB_THREADS >> 5),
+        (int)(tid_ % GSZ), (int)(tid_ / GSZ), (int)(DMB_THREADS / GSZ)};
+  unsigned bid_;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid_));
+  double* slot = a.ws + (size_t)bid_ * SLOT_DOUBLES;
   Inst I;
   bind_vectors(I, DMB_VEC_SMEM ? sm + SM_VEC : slot + SLOT_VEC);
   I.er = DMB_ERN_SMEM ? sm + SM_ER : slot + SLOT_ERN;
@@ -139,14 +151,14 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_sens_kernel(con
   I.lb = a.lbI; I.ub = a.ubI; I.df = 1.0; I.sub = nullptr;
   I.relax_fac = a.relax_fac; I.relax_max = a.relax_max;
   I.mbar = S->mbar; I.mphase = S->mphase;
-  if (threadIdx.x == 0) {
+  if (c.tid == 0) {
     for (int i = 0; i < DMB_NGRP; ++i) { mbar_init(S->mbar + i, 1); S->mphase[i] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const size_t nrow = a.mode == 1 ? NU : DMB_NW;
   while (true) {
-    if (threadIdx.x == 0) cur = atomicAdd(a.counter, 1);
+    if (c.tid == 0) cur = atomicAdd(a.counter, 1);
     __syncthreads();
     const int b = cur;
     __syncthreads();
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(DMB_THREADS, DMB_MIN_CTAS) dmb_sens_kernel(con
       sens_solve(c, I, a.max_refine, a.ratio_max, sm + SM_TILE, sm + SM_QS, S);
       sens_store(c, I, a.mode, dx, dl);
     }
-    if (threadIdx.x == 0 && a.sstat) a.sstat[b] = st;
+    if (c.tid == 0 && a.sstat) a.sstat[b] = st;
     __syncthreads();
   }
 }

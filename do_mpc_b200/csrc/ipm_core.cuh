@@ -388,7 +388,7 @@ DMB_DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsig
   const unsigned m = smem_u32(bar);
   asm volatile("fence.proxy.async;" ::: "memory");                     // earlier generic writes of the image (y0 column) -> async proxy
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
 }
 DMB_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
