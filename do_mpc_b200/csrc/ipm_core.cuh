@@ -965,8 +965,14 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
         }
         WARP_SYNC();
         const double sig = T[STG_SIGS + i], rd = T[STG_RD + i] + sig * tv[NVP];
-        for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) er[ER_HH + idx] += sig * tv[idx / NVP] * tv[idx % NVP];
-        for (int a = c.gl; a < NVP; a += GSZ) er[ER_GH + a] += tv[a] * rd;
+        // the inertia correction acts on the slacks as well (IPOPT: delta_s = delta_x): (Sigma_s + delta) takes the place of
+        // Sigma_s, so the delta-proportional parts join Y'Y / Y'y0, which the node assembly scales with delta
+        const double dms = (ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + NX + i]) + tv[NVP];
+        for (int idx = c.gl; idx < NVP * NVP; idx += GSZ) {
+          const double tt = tv[idx / NVP] * tv[idx % NVP];
+          er[ER_HH + idx] += sig * tt; er[ER_YTY + idx] += tt;
+        }
+        for (int a = c.gl; a < NVP; a += GSZ) { er[ER_GH + a] += tv[a] * rd; er[ER_YTY0 + a] += tv[a] * dms; }
         WARP_SYNC();
       }
     }
@@ -1414,7 +1420,7 @@ DMB_DEV void load_tile_image(const Ctx& c, const Inst& I, const double* eb, doub
 
 // recovery phase, data of one edge that does not depend on the roll-out: the [LU | Yext] tile image (one TMA bulk copy, tracked by
 // the group's mbarrier) and the sparse blocks, staged into the group's tile
-DMB_DEV void fr_stage_edge(const Ctx& c, const Inst& I, const double* res, int ls_mode, int refine, int gy_off, int e, bool act, double* T) {
+DMB_DEV void fr_stage_edge(const Ctx& c, const Inst& I, const double* res, double delta, int ls_mode, int refine, int gy_off, int e, bool act, double* T) {
   const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
 #if DMB_TMA
   if (act && c.gl == 0) tma_load_1d(T, eb + EB_IMG, IMG_SZ * 8, I.mbar + c.grp);       // one bulk copy in flight per lane group
@@ -1426,10 +1432,14 @@ DMB_DEV void fr_stage_edge(const Ctx& c, const Inst& I, const double* res, int l
     DMB_COPY_BATCH(NY, c.gl, GSZ, eb[EB_SIGY + idx], T[STG_SIGY + idx] = val);
 #if NNL > 0
     for (int i = c.gl; i < DMB_NNZ_D; i += GSZ) T[STG_DNZ + i] = eb[EB_DNZ + i];
-    // re-solve with a new right-hand side: r_d = Sigma_s rp_d (zero in a refinement solve, where the condensed rows are exact)
-    for (int i = c.gl; i < NNL; i += GSZ) { T[STG_SIGS + i] = eb[EB_SIGS + i]; T[STG_RD + i] = refine ? eb[EB_SIGS + i] * res[LAM_EDGE(e) + NY + NX + i] : eb[EB_RD + i]; }
+    // (Sigma_s + delta) in place of Sigma_s (inertia correction, see factor_edges).  Re-solve with a new right-hand side:
+    // r_d = (Sigma_s + delta) rp_d (zero in a refinement solve, where the condensed rows are exact)
+    for (int i = c.gl; i < NNL; i += GSZ) {
+      const double sg = eb[EB_SIGS + i] + delta, rr = ls_mode ? 0.0 : res[LAM_EDGE(e) + NY + NX + i];
+      T[STG_SIGS + i] = sg; T[STG_RD + i] = refine ? sg * rr : eb[EB_RD + i] + delta * rr;
+    }
 #else
-    (void)res; (void)refine;
+    (void)res; (void)refine; (void)delta;
 #endif
   }
 }
@@ -1446,7 +1456,7 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
   const bool early = !par && c.nwarp > 1;
   if (early && c.warp != 0) {
     const int e = c.grp;
-    fr_stage_edge(c, I, res, ls_mode, refine, gy_off, e, e < NEDGE, tile_base + (size_t)c.grp * TILE_SZ);
+    fr_stage_edge(c, I, res, delta, ls_mode, refine, gy_off, e, e < NEDGE, tile_base + (size_t)c.grp * TILE_SZ);
   }
   {
 #if DMB_NSCEN == 1 && !defined(DMB_HOSTSIM) && (NXI <= 8) && (NVP <= 8) && !defined(DMB_NO_CHAIN_ROLLOUT)
@@ -1554,7 +1564,7 @@ DMB_PHASE void forward_recover(const Ctx& c, const Inst& I, const double* res, d
     const int e = e0 + c.grp;
     const bool act = e < NEDGE;
     const double* eb = I.eb + (size_t)(act ? e : 0) * EB_SZ;
-    if (!(early && e0 == 0 && c.warp != 0)) fr_stage_edge(c, I, res, ls_mode, refine, gy_off, e, act, T);
+    if (!(early && e0 == 0 && c.warp != 0)) fr_stage_edge(c, I, res, delta, ls_mode, refine, gy_off, e, act, T);
     if (act) {
       const double* dvp = I.dw + NODE_OFF(EDGE_PARENT_OF(e));
       for (int i = c.gl; i < NVP; i += GSZ) dq[i] = dvp[i];

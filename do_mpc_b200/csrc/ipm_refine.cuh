@@ -54,7 +54,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
       for (int i = c.gl; i < NNL; i += GSZ) {
         double jd = 0.0;
         for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) jd += dz[t] * dq[DMB_D_COL[t]];
-        ydv[i] = eb[EB_SIGS + i] * jd + eb[EB_RD + i];                    // = y_d+ of the condensed system
+        ydv[i] = (eb[EB_SIGS + i] + delta) * jd + eb[EB_RD + i] + delta * res[LAM_EDGE(e) + NY + NX + i];   // = y_d+ of the condensed system
         rp[LAM_EDGE(e) + NY + NX + i] = 0.0;                               // eliminated exactly
       }
     WARP_SYNC();
@@ -170,7 +170,7 @@ DMB_PHASE void kkt_residual(const Ctx& c, const Inst& I, const double* res, doub
 // Overwrites ER_GH / ER_YTY0 / ER_B, the y0 column of the tile image (EB_IMG) and EB_GY (:= rd_y) — the primary values are no longer
 // needed once the primary step has been recovered (the primary g_y in EB_GY is kept for further residual evaluations).
 // ---------------------------------------------------------------------------------------------------
-DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
+DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double delta, double* tile_base) {
   const double* rd = I.gl; const double* rp = I.rest;
   double* T = tile_base + (size_t)c.grp * TILE_SZ;
   double* bv = T + STG_DQ;                      // NY: permuted rhs / solution
@@ -217,7 +217,7 @@ DMB_PHASE void resolve_edges(const Ctx& c, const Inst& I, double* tile_base) {
         for (int i = 0; i < NNL; ++i) {
           double jd = rp[LAM_EDGE(e) + NY + NX + i];          // right-hand side of the condensed row (0 in a refinement solve)
           for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) if (DMB_D_COL[t] >= NVP) jd += eb[EB_DNZ + t] * bv[DMB_D_COL[t] - NVP];
-          for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) z[DMB_D_COL[t]] += eb[EB_DNZ + t] * eb[EB_SIGS + i] * jd;
+          for (int t = DMB_DR_START[i]; t < DMB_DR_START[i + 1]; ++t) z[DMB_D_COL[t]] += eb[EB_DNZ + t] * (eb[EB_SIGS + i] + delta) * jd;
         }
 #endif
 #pragma unroll

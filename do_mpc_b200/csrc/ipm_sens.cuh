@@ -187,7 +187,7 @@ DMB_DEV void sens_solve(const Ctx& c, const Inst& I, int max_refine, double rati
     for (int i = c.tid; i < NLAM; i += c.nthr) I.lamr[i] = I.lamn[i];
     for (int i = c.tid; i < NEDGE * NNL; i += c.nthr) I.st[i] = I.ds[i];
     CTA_SYNC();
-    resolve_edges(c, I, tile);
+    resolve_edges(c, I, 0.0, tile);
     riccati_vector_t<true>(c, I, 0.0, Qs);
     forward_recover(c, I, I.rest, 0.0, 0, 1, tile);
     for (int i = c.tid; i < NWI; i += c.nthr) I.dw[i] += I.wt[i];

@@ -90,7 +90,7 @@ DMB_COLD void eval_point_cold(const Ctx c, const Inst I, const double* w, const 
 }
 // K [dw; lam+; ds] = -[rd; rp] with the factors of the current iteration: rd = I.gl, rp = I.rest  ->  I.dw, I.lamn, I.ds
 DMB_DEV void resolve_system(const Ctx& c, const Inst& I, double delta_w, double* tile, double* Qs) {
-  resolve_edges(c, I, tile);
+  resolve_edges(c, I, delta_w, tile);
   riccati_vector(c, I, delta_w, Qs);
   forward_recover(c, I, I.rest, delta_w, 0, 1, tile);
 }

@@ -537,6 +537,9 @@ class IPMSolver:
                     if accepted:
                         break
                 alpha *= o.alpha_red_factor
+            if o.verbose:
+                print(f"     alpha={alpha:.3e} a_max={a_max:.3e} a_z={a_z:.3e} ls={ls} dphi={dphi:.3e} phi={phi:.12e} accepted={int(accepted)} "
+                      f"armijo={int(armijo)} soc={int(soc_used)} delta_w={delta_w:.1e}")
             if not accepted:
                 # ---- restoration substitute ----
                 resto_count += 1

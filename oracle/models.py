@@ -11,6 +11,11 @@ reference template files configure.  Only the mathematics is restated; nothing i
   oscillating_masses_dae()  examples/oscillating_masses_discrete_dae/template_model.py:33-75, template_mpc.py:33-70
   dip()                 examples/double_inverted_pendulum/template_model.py:33-150, template_mpc.py:33-95
   industrial_poly()     examples/industrial_poly/template_model.py:33-125, template_mpc.py:33-105
+  kite()                examples/kite/template_model.py:33-85, template_mpc.py:33-90
+  kinematic_bicycle()   examples/kinematic_bicycle_model/template_model.py:33-70, template_mpc.py:33-85
+  dynamic_bicycle()     examples/dynamic_bicycle_model/template_model.py:33-95, template_mpc.py:33-90
+The last three have no golden in the reference's testing/results: their restatements are pinned only through the shared
+NLP assembly (oracle/nlp.py) that the six golden families pin.
 """
 import itertools
 
@@ -227,6 +232,60 @@ def industrial_poly(n_horizon=20, n_robust=1):
                   x_lb=[0.0, 0.0, 26.0, 363.15 - tr, 298.0, 298.0, 288.0, 288.0, 0.0, -inf], x_ub=x_ub,
                   u_lb=[0.0, 333.15, 333.15], u_ub=[3.0e4, 373.15, 373.15], nl_cons=nl,
                   p_scenarios=_scenarios([950.0, 950.0 * 1.30, 950.0 * 0.70], [7.0, 7.0 * 1.30, 7.0 * 0.70]))
+
+
+# ------------------------------------------------------------------------------------------------
+def kite(w_ref=10.0, E_0_nom=6.0, h_min=100.0, n_horizon=80):
+    """Towing kite: thrust maximisation through an aux expression that reads the uncertain parameters, soft height
+    constraint; n_robust = 0 (only the nominal combination of the three wind speeds enters the NLP)."""
+    L_tether, A, rho, beta, c_tilde = 400.0, 300.0, 1.0, 0.0, 0.028
+    theta, phi, psi, u_tilde, E_0, v_0 = sy.symbols("theta phi psi u_tilde E_0 v_0")
+    E = E_0 - c_tilde * u_tilde ** 2
+    v_a = v_0 * E * sy.cos(theta)
+    P_D = (rho * v_0 ** 2) / 2.0
+    T_F = (P_D * A * sy.cos(theta) ** 2 * (E + 1.0) * sy.sqrt(E ** 2 + 1.0)) * (sy.cos(theta) * np.cos(beta) + sy.sin(theta) * np.sin(beta) * sy.sin(phi))
+    height = L_tether * sy.sin(theta) * sy.cos(phi)
+    dphi = -v_a / (L_tether * sy.sin(theta)) * sy.sin(psi)
+    rhs = [v_a / L_tether * (sy.cos(psi) - sy.tan(theta) / E), dphi, v_a / L_tether * u_tilde + dphi * sy.cos(theta)]
+    m = ModelDef("continuous", x=[theta, phi, psi], u=[u_tilde], p=[E_0, v_0], rhs=rhs,
+                 aux={"E_0": E_0, "v_0": v_0, "T_F": T_F, "height_kite": height})
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.15, n_robust=0, collocation_deg=2, collocation_ni=1,
+                  lterm=-T_F / 1e4, mterm=sy.Integer(0), rterm_factor=[0.5],
+                  x_lb=[0.0, -0.5 * np.pi, -np.pi], x_ub=[0.5 * np.pi, 0.5 * np.pi, np.pi], u_lb=[-10], u_ub=[10],
+                  nl_cons=[NlCons("height_kite", -height, ub=-h_min, soft=True, penalty=1e3, max_violation=10)],
+                  p_scenarios=_scenarios([E_0_nom], [w_ref, w_ref * 0.8, w_ref * 1.2]))
+
+
+def kinematic_bicycle(n_horizon=10):
+    lf, lr = 0.3, 0.3
+    X_p, Y_p, Psi, V, Delta, Acc = sy.symbols("X_p Y_p Psi V Delta Acc")
+    Beta = sy.atan((lr / (lr + lf)) * sy.tan(Delta))
+    rhs = [V * sy.cos(Psi + Beta), V * sy.sin(Psi + Beta), (V / lr) * sy.sin(Beta), Acc]
+    m = ModelDef("continuous", x=[X_p, Y_p, Psi, V], u=[Delta, Acc], rhs=rhs)
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.05, n_robust=0, collocation_deg=2, collocation_ni=1,
+                  lterm=sy.Integer(0), mterm=(Y_p - 2) ** 2 + (X_p - 3) ** 2 + Psi ** 2, rterm_factor=[1.0, 1e-3],
+                  x_lb=[-50, -50, -np.pi / 2, -5], x_ub=[50, 50, np.pi / 2, 5], u_lb=[-5, -5], u_ub=[5, 5])
+
+
+def dynamic_bicycle(n_horizon=10):
+    mass, I_z, lf, lr = 5.692, 0.204, 0.178, 0.147
+    D_f, D_r, C_f, C_r, B_f, B_r = 134.585, 159.919, 0.085, 0.133, 9.242, 17.716
+    c_m1, c_m2, c_m3, c_m4 = 20, 6.92 * 1e-7, 3.99, 0.67
+    X_p, Y_p, Psi, V_x, V_y, W, Delta, d = sy.symbols("X_p Y_p Psi V_x V_y W Delta d")
+    alpha_f = -sy.atan2(W * lf + V_y, V_x) + Delta
+    alpha_r = sy.atan2(W * lr - V_y, V_x)
+    F_f_y = D_f * sy.sin(C_f * sy.atan(B_f * alpha_f))
+    F_r_y = D_r * sy.sin(C_r * sy.atan(B_r * alpha_r))
+    F_x = (c_m1 - c_m2 * V_x) * d - c_m4 * V_x ** 2 - c_m3
+    rhs = [V_x * sy.cos(Psi) - V_y * sy.sin(Psi), V_x * sy.sin(Psi) + V_y * sy.cos(Psi), W,
+           (1 / mass) * (F_x - F_f_y * sy.sin(Delta) + mass * V_y * W),
+           (1 / mass) * (F_r_y + F_f_y * sy.cos(Delta) - mass * V_x * W),
+           (1 / I_z) * (F_f_y * lf * sy.cos(Delta) - lf * F_x * sy.sin(Delta) - lr * F_r_y)]
+    m = ModelDef("continuous", x=[X_p, Y_p, Psi, V_x, V_y, W], u=[Delta, d], rhs=rhs, aux={"Vel": sy.sqrt(V_x ** 2 + V_y ** 2)})
+    cost = (Y_p - 1) ** 2
+    return MPCDef(m, n_horizon=n_horizon, t_step=0.1, n_robust=0, collocation_deg=2, collocation_ni=1,
+                  lterm=cost, mterm=cost, rterm_factor=[1e-3, 1e-3],
+                  x_lb=[-50000, -2, -0.78, 0.1, -1, -0.2], x_ub=[50000, 2, 0.78, 5, 1, 0.2], u_lb=[-2, 0], u_ub=[2, 1])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,8 +5,10 @@ import numpy as np
 from conftest import GOLDEN
 
 import batch_reactor
+import bicycle
 import dip
 import industrial_poly
+import kite
 import oscillating_masses
 
 CONFIGS = {
@@ -14,7 +16,13 @@ CONFIGS = {
     3: ("batch_reactor robust n_robust=1 N=30", lambda setup: batch_reactor.reactor_mpc(n_horizon=30, n_robust=1, setup=setup), (8082, 7564, 23)),
     4: ("DIP swing-up N=50", lambda setup: dip.dip_mpc(n_horizon=50, setup=setup), (2180, 2256, 76)),
     5: ("industrial_poly robust N=20", lambda setup: industrial_poly.poly_mpc(setup=setup), (8100, 7210, 31)),
+    # example families of the reference that ship no golden (sizes from running the reference's templates through compat/,
+    # tests/test_compat_templates.py): 32 initial states each around the example's main.py
+    "kite": ("towing kite N=80 (aux objective reading parameters, soft aux constraint)", lambda setup: kite.kite_mpc(setup=setup), (1132, 1043, 10)),
+    "kinbike": ("kinematic bicycle N=10", lambda setup: bicycle.kinematic_mpc(setup=setup), (196, 164, 6)),
+    "dynbike": ("dynamic bicycle N=10 (Pacejka tyre forces, atan2)", lambda setup: bicycle.dynamic_mpc(setup=setup), (284, 246, 8)),
 }
+EXAMPLE_FAMILIES = ("kite", "kinbike", "dynbike")
 MAX_ITER = 300
 
 

@@ -20,7 +20,9 @@ import numpy as np
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
-MAX_ITER = {1: 300, 3: 300, 4: 300, 5: 300}
+MAX_ITER = {1: 300, 3: 300, 4: 300, 5: 300, "kite": 300, "kinbike": 300, "dynbike": 300}
+# example families of the reference without a golden in testing/results (examples/kite, kinematic_bicycle_model,
+# dynamic_bicycle_model): fixtures "cfgkite", "cfgkinbike", "cfgdynbike", initial states drawn around main.py's
 
 
 def config_inputs(cfg, n):
@@ -41,6 +43,20 @@ def config_inputs(cfg, n):
         g = np.load(os.path.join(ROOT, "tests", "golden", "kkt_industrial_poly.npz"))
         x0 = g["x"][0] * rng.uniform(0.98, 1.02, size=(2048, 10))
         return x0[:n], np.zeros((n, 3)), None, None
+    if cfg == "kite":
+        # examples/kite/main.py:44-56: each state uniformly inside 60 % of its bounds; w_ref / E_0 / h_min fixed to 10 / 6 / 100
+        lo, hi = np.array([0.0, -0.5 * np.pi, -np.pi]), np.array([0.5 * np.pi, 0.5 * np.pi, np.pi])
+        m_, r_ = (hi + lo) / 2, (hi - lo) / 2
+        x0 = m_ - 0.6 * r_ + 2 * 0.6 * r_ * rng.uniform(size=(64, 3))
+        return x0[:n], np.zeros((n, 1)), None, None
+    if cfg == "kinbike":
+        # examples/kinematic_bicycle_model/main.py:45-50: x0 = (0, 0, 0, 0.1), perturbed
+        x0 = np.array([0.0, 0.0, 0.0, 0.1]) + rng.uniform([-1, -1, -0.5, 0.0], [1, 1, 0.5, 2.0], size=(64, 4))
+        return x0[:n], np.zeros((n, 2)), None, None
+    if cfg == "dynbike":
+        # examples/dynamic_bicycle_model/main.py:57-64: x0 = (0, 0, 0, 0.1, 0, 0), perturbed inside the state bounds
+        x0 = np.array([0.0, 0.0, 0.0, 0.1, 0.0, 0.0]) + rng.uniform([-1, -0.5, -0.3, 0.0, -0.2, -0.1], [1, 0.5, 0.3, 2.0, 0.2, 0.1], size=(64, 6))
+        return x0[:n], np.zeros((n, 2)), None, None
     raise ValueError(cfg)
 
 
@@ -48,7 +64,8 @@ def config_nlp(cfg):
     from oracle import models
     from oracle.nlp import FlatNLP
     d = {1: lambda: models.oscillating_masses(10), 3: lambda: models.batch_reactor(30, 1), 4: lambda: models.dip(50),
-         5: lambda: models.industrial_poly(20, 1)}[cfg]()
+         5: lambda: models.industrial_poly(20, 1), "kite": models.kite, "kinbike": models.kinematic_bicycle,
+         "dynbike": models.dynamic_bicycle}[cfg]()
     return FlatNLP(d)
 
 
@@ -72,7 +89,7 @@ def _work(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cfgs", nargs="*", type=int, default=[1, 3, 4, 5])
+    ap.add_argument("cfgs", nargs="*", type=lambda v: int(v) if v.isdigit() else v, default=[1, 3, 4, 5])
     ap.add_argument("--n", type=int, default=64)
     ap.add_argument("--procs", type=int, default=os.cpu_count() or 1)
     a = ap.parse_args()

@@ -115,3 +115,42 @@ def test_reference_rotating_masses_templates_with_mhe(compat_path, monkeypatch):
     va = E.evaluate(a.G.ids() + a.lterm.ids() + a.nl.ids(), dict(zip(a.q.ids() + a.tvp.ids() + a.pp.ids(), np.concatenate([q, tv, pp]))))
     vb = E.evaluate(b.G.ids() + b.lterm.ids() + b.nl.ids(), dict(zip(b.q.ids() + b.tvp.ids() + b.pp.ids(), np.concatenate([q, tv, pp]))))
     assert np.allclose(va, vb, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("ex,args,mine", [("kite", (10.0, 6.0, 100.0), "kite.kite_mpc"), ("kinematic_bicycle_model", (), "bicycle.kinematic_mpc"),
+                                          ("dynamic_bicycle_model", (), "bicycle.dynamic_mpc")])
+def test_reference_templates_without_golden_equal_this_repos_examples(compat_path, monkeypatch, ex, args, mine):
+    """examples/kite, kinematic_bicycle_model, dynamic_bicycle_model (no golden in testing/results): the reference's templates
+    build, through compat/, the same stage recipe as examples/kite.py / examples/bicycle.py — the controllers that the oracle
+    fixtures tests/golden/cfg{kite,kinbike,dynbike}_oracle.npz pin on the CPU emulation and on the GPU."""
+    import importlib
+    from do_mpc_b200.controller import MPC
+    from do_mpc_b200.simulator import Simulator
+    monkeypatch.setattr(MPC, "setup", _setup_without_gpu)
+    monkeypatch.setattr(Simulator, "setup", lambda self: self.settings.check_for_mandatory_settings())
+    sys.path.insert(0, str(REF / ex))                       # kite/template_simulator.py imports its wind_model module
+    try:
+        model = _load(REF / ex / "template_model.py", f"ref_{ex}_model").template_model()
+        mpc = _load(REF / ex / "template_mpc.py", f"ref_{ex}_mpc").template_mpc(model, *args, silence_solver=True)
+        ts = _load(REF / ex / "template_simulator.py", f"ref_{ex}_sim")
+        sim = ts.template_simulator(model, *args[:2])
+    finally:
+        sys.path.remove(str(REF / ex))
+    assert sim.settings.t_step == mpc.settings.t_step
+    mod, fn = mine.split(".")
+    own = getattr(importlib.import_module(mod), fn)(setup=False); own.prepare_nlp()
+    a, b = mpc.recipe, own.recipe
+    assert (a.n_w, a.n_g, a.n_p) == (b.n_w, b.n_g, b.n_p)
+    from do_mpc_b200.sym import expr as E
+    rng = np.random.RandomState(0)
+    syms = lambda r: sum(([] if v is None else v.ids() for v in (r.q, r.tvp, r.pp, r.uprev, r.xN)), [])
+    vals = np.concatenate([rng.uniform(0.3, 1.2, size=a.q.numel()), rng.uniform(0.5, 1.5, size=a.tvp.numel()),
+                           rng.uniform(5.0, 7.0, size=a.pp.numel()), rng.uniform(0.3, 1.2, size=a.uprev.numel() + a.xN.numel())])
+    ids = lambda r: sum((v.ids() for v in (r.G, r.lterm, r.mterm, r.rterm, r.nl) if v is not None and v.numel()), [])
+    assert len(syms(a)) == len(syms(b)) == len(vals)
+    va = E.evaluate(ids(a), dict(zip(syms(a), vals)))
+    vb = E.evaluate(ids(b), dict(zip(syms(b), vals)))
+    assert len(va) == len(vb) > 0
+    assert np.allclose(va, vb, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(mpc._lb_opt_x.full(), own._lb_opt_x.full()) and np.array_equal(mpc._ub_opt_x.full(), own._ub_opt_x.full())
+    assert np.array_equal(np.asarray(mpc.nlp_cons_ub), np.asarray(own.nlp_cons_ub))

@@ -7,10 +7,11 @@ import pytest
 from conftest import HostSim
 from config_cases import MAX_ITER, compare_with_oracle, config_mpc, fixture
 
-CASES = {1: np.arange(64), 3: np.array([0, 1]), 4: np.array([0, 1, 2]), 5: np.array([0, 1, 2, 3])}
+CASES = {1: np.arange(64), 3: np.array([0, 1]), 4: np.array([0, 1, 2]), 5: np.array([0, 1, 2, 3]),
+         "kite": np.arange(32), "kinbike": np.arange(32), "dynbike": np.arange(32)}
 
 
-@pytest.mark.parametrize("cfg", [1, 3, 4, 5])
+@pytest.mark.parametrize("cfg", [1, 3, 4, 5, "kite", "kinbike", "dynbike"])
 def test_config_matches_oracle_fixture(cfg):
     mpc = config_mpc(cfg, setup=False)
     fx = fixture(cfg)
