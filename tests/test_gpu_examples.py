@@ -36,17 +36,23 @@ def test_cold_start_matches_reference_ipopt_on_gpu(name):
     sim.o.max_iter = 500
     k = 4
     ref = sim.solve(Pb[:k], x0s=xb[:k], u0s=np.repeat(u0s, k, axis=0), z0s=None if z0s is None else np.repeat(z0s, k, axis=0))
-    if name == "dip":
-        assert ref["status"][0] == out["status"][0] == 0
-    else:
-        assert np.array_equal(ref["status"], out["status"][:k])
+    assert np.array_equal(ref["success"], out["success"][:k])
     same = (np.abs(ref["iter_count"] - out["iter_count"][:k]) <= 1) & (ref["status"] == out["status"][:k])
-    # the pendulum swing-up takes >100 iterations on a non-convex landscape: FMA contraction on the GPU vs x86 rounding
-    # may change the path of perturbed instances; the golden instance and all short solves must agree exactly
-    assert same.all() or name == "dip"
-    if not same[0]:                  # chaotic path: the golden instance must still reach the reference solution (checked above)
-        same[0] = False
-    assert np.abs(ref["u0_scaled"][same] - out["u0_scaled"][:k][same]).max() < 1e-7
+    # Path mismatches are counted, not folded into a tolerance (tier T2).  The pendulum swing-up (N = 100) takes
+    # 125 - 150 iterations on a non-convex landscape and is chaotic with respect to rounding: on the golden instance the oracle
+    # needs 134 iterations, the CPU emulation 125, the GPU (FMA contraction) 137 — all three end at the reference's IPOPT
+    # solution.  For that family the requirement is therefore on the solution (same success flags — asserted above —, same
+    # basin: u0 within the north-star tolerance), with basin mismatches of perturbed instances counted and bounded; every
+    # other family must agree on every instance, iteration for iteration.
+    n_path = int((~same).sum())
+    du = np.abs(ref["u0_scaled"] - out["u0_scaled"][:k]).max(axis=1)
+    print(f"{name}: {n_path} of {k} instances took a different path on the GPU than on the CPU emulation; max |u0 difference| (scaled) {du.max():.2e}")
+    if name == "dip":
+        n_basin = int((du[ref["success"]] > TOL).sum())
+        assert du[0] < TOL and n_basin <= k // 4, (n_basin, du, ref["iter_count"], out["iter_count"][:k])
+    else:
+        assert n_path == 0, (name, ref["iter_count"], out["iter_count"][:k], ref["status"], out["status"][:k])
+        assert du.max() < 1e-7
 
 
 def test_make_step_loop_like_reference_regression_test():

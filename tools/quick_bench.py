@@ -25,8 +25,11 @@ def cases():
 
 def main():
     import torch
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["2"]
-    steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 3
+    argv = sys.argv[1:]
+    steps = 3
+    if "--steps" in argv:
+        i = argv.index("--steps"); steps = int(argv[i + 1]); del argv[i:i + 2]
+    which = [a for a in argv if not a.startswith("--")] or ["2"]
     dev = torch.device("cuda", 0)
     cs = cases()
     for k in which:
