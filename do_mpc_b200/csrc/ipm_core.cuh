@@ -150,6 +150,17 @@ enum DmbStatus {
 // LU tile of a group: NY rows x [G_y (NY) | G_vp,rhs (NE) | M_ext (NE)], a compact NVP x NE block N = H_vy*Yext, and a
 // staging area for the bulk per-edge data (global loads never sit inside dependent inner loops)
 #define TILE_NC (NY + NE)
+// Lane-flattened LU update / back substitution of the factor phase (all lanes of a group share the entries of a step instead
+// of one lane per row / per right-hand side): fewer dependent steps per lane but more instructions.  Measured on B200
+// (profiles/r2_flat_lu_ab.json): DIP N=50 (chain, NY = 27) +8.8 % / +1.5 %, batch reactor tree (NY = 20) -1.4 % / -6 %,
+// industrial_poly tree -12 % with both, CSTR (NY = 12, two groups per warp) -0.5 %: it pays where the kernel is latency bound
+// (one scenario) and the blocks are large; scenario trees have enough warps in flight and are bound by instruction issue.
+#ifndef DMB_LU_FLAT
+#define DMB_LU_FLAT (DMB_NSCEN == 1 && DMB_NY > 16)
+#endif
+#ifndef DMB_BS_FLAT
+#define DMB_BS_FLAT (DMB_NSCEN == 1 && DMB_NY > 16)
+#endif
 #define TILE_M (NY + NE)
 #define TILE_LD ((NY + 2 * NE) | 1)                   // odd leading dimension: conflict-free 64-bit rows
 #define STG_N (NY * TILE_LD)                           // N block, row-major NVP x NE
@@ -728,6 +739,32 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
         const double t = T[STG_PERM + k]; T[STG_PERM + k] = T[STG_PERM + pr]; T[STG_PERM + pr] = t;
       }
       WARP_SYNC();
+#if DMB_LU_FLAT
+      // multipliers first, then the rank-1 update with its (NY-1-k) x (TILE_NC-1-k) entries dealt out over ALL lanes of the
+      // group: with one lane per row the lanes of the rows <= k idle (on average half of the NY active ones, and GSZ - NY never
+      // work).  Same operation per entry as the row loop (t -= l * u), so the factors are bit-identical.
+      if (act) {
+        const double pv = T[k * TILE_LD + k];
+        if (!(fabs(pv) > 1e-300)) *fail = 1;
+        const double inv = 1.0 / pv;
+        for (int r = k + 1 + c.gl; r < NY; r += GSZ) T[r * TILE_LD + k] *= inv;
+        if (c.gl == 0) T[STG_INVD + k] = inv;
+      }
+      WARP_SYNC();
+      if (act) {
+        const int nc = TILE_NC - 1 - k, n = (NY - 1 - k) * nc;
+        const float rnc = 1.0f / (float)nc;                 // idx / nc through the reciprocal (exact for these small integers)
+        const double* urow = T + k * TILE_LD + k + 1;
+#pragma unroll 4
+        for (int idx = c.gl; idx < n; idx += GSZ) {
+          const int r = (int)(((float)idx + 0.5f) * rnc), cc = idx - r * nc;
+          double* row = T + (k + 1 + r) * TILE_LD + k;
+          row[1 + cc] -= row[0] * urow[cc];
+        }
+      }
+      WARP_SYNC();
+    }
+#else
       if (act) {
         const double pv = T[k * TILE_LD + k];
         if (!(fabs(pv) > 1e-300)) *fail = 1;
@@ -742,7 +779,27 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
       }
       WARP_SYNC();
     }
+#endif
     SUB_TICK(I, 1);
+#if NY > 16 && DMB_BS_FLAT
+    // ---- back substitution as a column sweep over ALL lanes of the group (one lane per right-hand side keeps NE of the 32
+    //      lanes busy): x_k = b_k / u_kk, then b_r -= u_rk x_k for the k * NE entries above; then Yext = [-X | x_rhs] ----------
+    if (act) for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
+    for (int k = NY - 1; k >= 0; --k) {
+      if (act) for (int j = c.gl; j < NE; j += GSZ) T[k * TILE_LD + NY + j] *= T[STG_INVD + k];
+      WARP_SYNC();
+      if (act) {
+        const double* xk = T + k * TILE_LD + NY;
+#pragma unroll 4
+        for (int idx = c.gl; idx < k * NE; idx += GSZ) {
+          const int r = idx / NE, j = idx - r * NE;
+          T[r * TILE_LD + NY + j] -= T[r * TILE_LD + k] * xk[j];
+        }
+      }
+      WARP_SYNC();
+    }
+    if (act) for (int idx = c.gl; idx < NY * NVP; idx += GSZ) { const int r = idx / NVP, j = idx - r * NVP; T[r * TILE_LD + NY + j] = -T[r * TILE_LD + NY + j]; }
+#else
     if (act) {
       for (int i = c.gl; i < NY; i += GSZ) eb[EB_PIV + i] = T[STG_PERM + i];
       // ---- back substitution, one lane per right-hand side; then Yext = [-X | x_rhs] --------------------------------
@@ -770,6 +827,7 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
 #endif
       }
     }
+#endif
     WARP_SYNC();
     SUB_TICK(I, 2);
     if (act) {
