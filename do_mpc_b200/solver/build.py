@@ -65,7 +65,7 @@ def _config_for(r: Recipe, src: str, threads: int):
     return fixed, ern_smem, vec_smem, total
 
 
-def launch_config(r: Recipe, src: str):
+def launch_config(r: Recipe, src: str, threads: int = None):
     """(threads per CTA, reduced blocks + node data in shared memory?, iterate vectors in shared memory?, CTAs/SM the
     register budget is compiled for).  227 KB of shared memory per SM on sm_100.  Measured on B200 (cfg #2):
       * 3 CTAs/SM with the iterate vectors in the L1/L2-backed slot beat 2 CTAs/SM with everything on chip (132.6k vs 110.6k),
@@ -86,7 +86,9 @@ def launch_config(r: Recipe, src: str):
         ctas = max(1, min(4, int(227 // total), 65536 // (threads * 128)))
         return (-(-n_edge // (threads // gsz)), threads, ern_smem, vec_smem, ctas)
 
-    if "DMB_FORCE_THREADS" in os.environ:                  # tuning experiments only
+    if threads is not None:                                # explicit CTA size (latency build, see BatchedNlpSolver)
+        best = cfg(int(threads))
+    elif "DMB_FORCE_THREADS" in os.environ:                # tuning experiments only
         best = cfg(int(os.environ["DMB_FORCE_THREADS"]))
     else:
         best = cfg(128) or cfg(64)
