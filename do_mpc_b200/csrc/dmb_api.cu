@@ -43,6 +43,7 @@
 #define SLOT_EB ((SLOT_ERN + (DMB_ERN_SMEM ? 0 : ERN_DOUBLES) + 1) & ~1)      // even: edge blocks 16-byte aligned (TMA)
 #define SLOT_DOUBLES (SLOT_EB + NEDGE * EB_SZ)
 static_assert(DMB_NGRP <= 16, "DmbShared holds 16 TMA barriers");
+static_assert(7 * DMB_NWARP <= 64, "DmbShared::red holds the 7 values of the largest fused reduction for at most 9 warps");
 static_assert(SLOT_DOUBLES % 2 == 0 && EB_SZ % 2 == 0 && TILE_SZ % 2 == 0, "TMA bulk copies need 16-byte aligned tiles and edge blocks");
 
 struct KernelArgs {

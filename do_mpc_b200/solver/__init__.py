@@ -15,7 +15,7 @@ from typing import Optional
 import numpy as np
 
 from ..sym.sx import DM
-from .build import build_library
+from .build import build_library, latency_threads
 from .options import DmbOptions, apply_nlpsol_opts
 
 _STATUS_NAMES = {0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", 2: "Infeasible_Problem_Detected",
@@ -66,9 +66,25 @@ def load_library(path):
 
 
 class BatchedNlpSolver:
-    def __init__(self, recipe, nlpsol_opts=None, device: Optional[int] = None):
+    """One generated library = one CTA size.  The solver owns the *throughput* build (several instances per SM) and, where a
+    larger CTA shortens the edge loops of an instance (build.latency_threads), creates a *latency* build on first use: batches of
+    at most `latency_max_batch` instances — the reference's real-time `make_step(x0)` is B = 1 — are solved by it with one
+    instance per SM.  Same kernel source, same options and bounds; `launch_info()` reports the build used last."""
+
+    def __init__(self, recipe, nlpsol_opts=None, device: Optional[int] = None, _threads: Optional[int] = None):
+        import os
+        from .codegen import generate
         self.recipe = recipe
-        self.lib_path = build_library(recipe)
+        src = generate(recipe)
+        self.lib_path = build_library(recipe, src=src, threads=_threads)
+        self._lat: Optional["BatchedNlpSolver"] = None          # the latency build, created lazily
+        self._lat_threads = None
+        self.latency_max_batch = 0
+        if _threads is None:
+            self.latency_max_batch = int(os.environ.get("DMB_LATENCY_MAX_BATCH", "16"))
+            if self.latency_max_batch > 0:
+                self._lat_threads = latency_threads(recipe, src)
+        self._last = self
         self.lib = load_library(self.lib_path)
         dims = (ctypes.c_int * DIM_COUNT)()
         self.lib.dmb_get_dims(dims)
@@ -81,7 +97,6 @@ class BatchedNlpSolver:
         self.lib.dmb_default_options(ctypes.byref(self.options))
         apply_nlpsol_opts(self.options, nlpsol_opts)
         if device is None:
-            import os
             device = int(os.environ.get("LOCAL_RANK", "0")) if "DMB_DEVICE" not in os.environ else int(os.environ["DMB_DEVICE"])
         self.device = device
         self._h = self.lib.dmb_create(device)
@@ -114,6 +129,23 @@ class BatchedNlpSolver:
             setattr(self.options, k, v)
         self._check(self.lib.dmb_set_options(self._h, ctypes.byref(self.options), ctypes.sizeof(DmbOptions)))
         self._bounds_key = None
+        if self._lat is not None:
+            self._lat.set_options(**kw)
+
+    def _for_batch(self, B):
+        """The build that solves a batch of B instances: the latency build for small batches (if the problem has one)."""
+        if self._lat_threads is None or B > self.latency_max_batch:
+            self._last = self
+            return self
+        if self._lat is None:
+            self._lat = BatchedNlpSolver(self.recipe, None, self.device, _threads=self._lat_threads)
+            ctypes.memmove(ctypes.byref(self._lat.options), ctypes.byref(self.options), ctypes.sizeof(DmbOptions))
+            self._lat.set_options()
+            self._lat.bounds_source = self.bounds_source
+        if self._bounds_key is not None and self._lat._bounds_key != self._bounds_key:
+            self._lat._set_bounds(np.frombuffer(self._bounds_key[0]), np.frombuffer(self._bounds_key[1]))
+        self._last = self._lat
+        return self._lat
 
     def _set_bounds(self, lbx, ubx):
         lbx = np.ascontiguousarray(np.asarray(lbx, dtype=np.float64).ravel())
@@ -142,6 +174,9 @@ class BatchedNlpSolver:
         B = P.shape[0]
         if lbx is not None:
             self._set_bounds(lbx, ubx)
+        S = self._for_batch(B)
+        if S is not self:
+            return S.solve_batch(P, x0s, u0s, z0s, None, None, x_init, return_full, lam_g0, lam_x0)
         x_init = None if x_init is None else _as2d(x_init, self.n_w)
         x0s = None if x0s is None else _as2d(x0s, self.n_x)
         u0s = None if u0s is None else _as2d(u0s, self.n_u)
@@ -174,6 +209,9 @@ class BatchedNlpSolver:
         import torch
         self._refresh_bounds(lbx, ubx)
         B = P.shape[0]
+        S = self._for_batch(B)
+        if S is not self:
+            return S.solve_batch_device(P, x0s, u0s, z0s, x_init, out, stream, want_full, lam_g0, lam_x0)
         dev = P.device
         def dp(t): return None if t is None else ctypes.c_void_p(t.data_ptr())
         if out is None:
@@ -262,6 +300,8 @@ class BatchedNlpSolver:
         return {"dxdp_t": dx, "sens_status": sst}
 
     def launch_info(self):
+        if self._last is not self:
+            return self._last.launch_info()
         grid = ctypes.c_int(); block = ctypes.c_int(); smem = ctypes.c_int(); n = ctypes.c_longlong(); ms = ctypes.c_float()
         self.lib.dmb_get_stats(self._h, ctypes.byref(grid), ctypes.byref(block), ctypes.byref(smem), ctypes.byref(n), ctypes.byref(ms))
         return {"grid": grid.value, "block": block.value, "smem_bytes": smem.value, "n_launches": n.value, "last_kernel_ms": ms.value}

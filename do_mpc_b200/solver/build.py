@@ -105,11 +105,42 @@ def launch_config(r: Recipe, src: str, threads: int = None):
     return threads, ern_smem, vec_smem, min_ctas
 
 
-def build_library(r: Recipe, verbose: bool = False, src: str = None) -> Path:
+MAX_LATENCY_THREADS = 256      # 8 warps: the CTA-wide reductions keep 7 values x warps in DmbShared::red[64] (csrc/ipm_solve.cuh)
+
+
+def latency_threads(r: Recipe, src: str):
+    """CTA size of the *latency build* of a problem, or None if a larger CTA would not shorten the edge loops.
+
+    The throughput rule above sizes a CTA so that 3-4 instances share an SM (registers capped at 128); a single instance (the
+    reference's real-time `make_step(x0)`) then runs on one CTA of 128-160 threads and walks through its edges in many rounds of
+    lane groups.  The latency build gives one instance more of an SM: up to 256 threads, compiled for one CTA per SM without a
+    register cap; it is used for small batches (BatchedNlpSolver.latency_max_batch).  Measured on B200, cold start, B = 1
+    (profiles/r2_latency_threads.json, 256 threads): robust CSTR (180 edges) 34.3 -> 18.8 ms, batch reactor tree N=30 (270 edges)
+    85.5 -> 45.4 ms (30.3 ms with 512 threads, which the reduction scratch does not support yet), nominal CSTR (20 edges, 2 rounds
+    either way) 2.10 -> 1.82 ms; identical iteration counts.  Rule: the CTA size <= 256 with the fewest rounds (the smallest
+    among equals), if that saves at least a quarter of the rounds of the throughput build."""
+    gsz = 16 if r.n_y <= 16 else 32
+    base = launch_config(r, src)[0]
+    n_edge = len(r.edge_k)
+    rounds = lambda t: -(-n_edge // (t // gsz))
+    best = None
+    for threads in range(base + 32, MAX_LATENCY_THREADS + 1, 32):
+        fixed, ern_smem, vec_smem, total = _config_for(r, src, threads)
+        if 8 * fixed > 220 * 1024 or total > 226:
+            continue
+        if best is None or rounds(threads) < rounds(best):
+            best = threads
+    if best is None or 4 * rounds(best) > 3 * rounds(base):
+        return None
+    return best
+
+
+def build_library(r: Recipe, verbose: bool = False, src: str = None, threads: int = None) -> Path:
     """Generated problem library of a stage recipe (in-tree cache).  `src`: the already generated problem_gen.h (lets a caller
-    generate serially — the symbolic engine is not thread safe — and compile several libraries concurrently)."""
+    generate serially — the symbolic engine is not thread safe — and compile several libraries concurrently).  `threads`: CTA
+    size of the latency build (one CTA per SM, see latency_threads); None = the throughput rule."""
     src = generate(r) if src is None else src
-    threads, ern_smem, vec_smem, min_ctas = launch_config(r, src)
+    threads, ern_smem, vec_smem, min_ctas = launch_config(r, src, threads=threads)[:4] if threads is None else (*launch_config(r, src, threads=threads)[:3], 1)
     extra = os.environ.get("DMB_EXTRA_NVCC_FLAGS", "").split()          # tuning experiments only
     key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{ern_smem}{vec_smem}{min_ctas}{extra}").encode()).hexdigest()[:16]
     d = CACHE / key
