@@ -71,11 +71,11 @@ class BatchedNlpSolver:
     at most `latency_max_batch` instances — the reference's real-time `make_step(x0)` is B = 1 — are solved by it with one
     instance per SM.  Same kernel source, same options and bounds; `launch_info()` reports the build used last."""
 
-    def __init__(self, recipe, nlpsol_opts=None, device: Optional[int] = None, _threads: Optional[int] = None):
+    def __init__(self, recipe, nlpsol_opts=None, device: Optional[int] = None, _threads: Optional[int] = None, _src: Optional[str] = None):
         import os
         from .codegen import generate
         self.recipe = recipe
-        src = generate(recipe)
+        src = self._src = generate(recipe) if _src is None else _src
         self.lib_path = build_library(recipe, src=src, threads=_threads)
         self._lat: Optional["BatchedNlpSolver"] = None          # the latency build, created lazily
         self._lat_threads = None
@@ -138,7 +138,7 @@ class BatchedNlpSolver:
             self._last = self
             return self
         if self._lat is None:
-            self._lat = BatchedNlpSolver(self.recipe, None, self.device, _threads=self._lat_threads)
+            self._lat = BatchedNlpSolver(self.recipe, None, self.device, _threads=self._lat_threads, _src=self._src)
             ctypes.memmove(ctypes.byref(self._lat.options), ctypes.byref(self.options), ctypes.sizeof(DmbOptions))
             self._lat.set_options()
             self._lat.bounds_source = self.bounds_source
