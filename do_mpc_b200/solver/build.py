@@ -140,7 +140,10 @@ def build_library(r: Recipe, verbose: bool = False, src: str = None, threads: in
     generate serially — the symbolic engine is not thread safe — and compile several libraries concurrently).  `threads`: CTA
     size of the latency build (one CTA per SM, see latency_threads); None = the throughput rule."""
     src = generate(r) if src is None else src
-    threads, ern_smem, vec_smem, min_ctas = launch_config(r, src, threads=threads)[:4] if threads is None else (*launch_config(r, src, threads=threads)[:3], 1)
+    latency = threads is not None
+    threads, ern_smem, vec_smem, min_ctas = launch_config(r, src, threads=threads)
+    if latency:
+        min_ctas = 1                                        # one CTA per SM: no register cap
     extra = os.environ.get("DMB_EXTRA_NVCC_FLAGS", "").split()          # tuning experiments only
     key = hashlib.sha256((src + _kernel_sources_digest() + f"{threads}{ern_smem}{vec_smem}{min_ctas}{extra}").encode()).hexdigest()[:16]
     d = CACHE / key
