@@ -6,6 +6,7 @@ from conftest import GOLDEN
 
 import batch_reactor
 import bicycle
+import cstr
 import dip
 import industrial_poly
 import kite
@@ -21,8 +22,14 @@ CONFIGS = {
     "kite": ("towing kite N=80 (aux objective reading parameters, soft aux constraint)", lambda setup: kite.kite_mpc(setup=setup), (1132, 1043, 10)),
     "kinbike": ("kinematic bicycle N=10", lambda setup: bicycle.kinematic_mpc(setup=setup), (196, 164, 6)),
     "dynbike": ("dynamic bicycle N=10 (Pacejka tyre forces, atan2)", lambda setup: bicycle.dynamic_mpc(setup=setup), (284, 246, 8)),
+    # golden families away from their golden initial state: random starts (CPU-emulation tests only)
+    "cstrrob": ("robust CSTR (tree + soft constraint), random starts", lambda setup: cstr.cstr_robust_mpc(setup=setup), (3564, 3064, 24)),
+    "reactor": ("batch reactor N=20, random starts", lambda setup: batch_reactor.reactor_mpc(setup=setup), (608, 564, 23)),
+    "polynom": ("industrial_poly without the tree (soft T_R constraint), random starts", lambda setup: industrial_poly.poly_mpc(n_robust=0, setup=setup), None),
+    "oscdae": ("discrete DAE oscillating masses, random starts", lambda setup: oscillating_masses.osc_dae_mpc(setup=setup), (67, 60, 5)),
 }
 EXAMPLE_FAMILIES = ("kite", "kinbike", "dynbike")
+RANDOM_START_FAMILIES = ("cstrrob", "reactor", "polynom", "oscdae")
 MAX_ITER = 300
 
 
@@ -37,7 +44,7 @@ def config_mpc(cfg, setup):
     if not setup:
         mpc.prepare_nlp()
     r = mpc.recipe
-    assert (r.n_w, r.n_g, r.n_p) == sizes, (name, (r.n_w, r.n_g, r.n_p))
+    assert sizes is None or (r.n_w, r.n_g, r.n_p) == sizes, (name, (r.n_w, r.n_g, r.n_p))
     return mpc
 
 

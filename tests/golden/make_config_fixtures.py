@@ -20,7 +20,8 @@ import numpy as np
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
-MAX_ITER = {1: 300, 3: 300, 4: 300, 5: 300, "kite": 300, "kinbike": 300, "dynbike": 300}
+MAX_ITER = {1: 300, 3: 300, 4: 300, 5: 300, "kite": 300, "kinbike": 300, "dynbike": 300, "cstrrob": 300, "reactor": 300, "oscdae": 300,
+            "polynom": 300}
 # example families of the reference without a golden in testing/results (examples/kite, kinematic_bicycle_model,
 # dynamic_bicycle_model): fixtures "cfgkite", "cfgkinbike", "cfgdynbike", initial states drawn around main.py's
 
@@ -57,6 +58,21 @@ def config_inputs(cfg, n):
         # examples/dynamic_bicycle_model/main.py:57-64: x0 = (0, 0, 0, 0.1, 0, 0), perturbed inside the state bounds
         x0 = np.array([0.0, 0.0, 0.0, 0.1, 0.0, 0.0]) + rng.uniform([-1, -0.5, -0.3, 0.0, -0.2, -0.1], [1, 0.5, 0.3, 2.0, 0.2, 0.1], size=(64, 6))
         return x0[:n], np.zeros((n, 2)), None, None
+    # golden families away from their golden initial state (random starts; CPU-emulation tests only, tests/test_hostsim_configs.py)
+    if cfg == "cstrrob":       # shipped robust CSTR (tree + soft constraint), x0 / u_prev from cfg #2's sampling box: 4 of 16 infeasible
+        r5 = np.random.RandomState(5)
+        return r5.uniform([0.1, 0.1, 50, 50], [2, 2, 140, 140], size=(16, 4))[:n], r5.uniform([5, -8500], [100, 0], size=(16, 2))[:n], None, None
+    if cfg in ("reactor", "polynom", "oscdae"):
+        r11 = np.random.RandomState(11)
+        x_r = np.array([1.0, 0.5, 0.0, 120.0]) * r11.uniform(0.7, 1.3, size=(16, 4)); u_r = r11.uniform(0, 0.2, size=(16, 1))
+        g = np.load(os.path.join(ROOT, "tests", "golden", "kkt_industrial_poly.npz"))
+        x_p = g["x"][0] * r11.uniform(0.995, 1.005, size=(8, 10))
+        x_o = r11.uniform(-1.5, 1.5, size=(32, 4)); u_o = r11.uniform(-1, 1, size=(32, 1))
+        if cfg == "reactor":   # shipped batch reactor (N=20, two finite elements), +-30 % around the golden start
+            return x_r[:n], u_r[:n], None, None
+        if cfg == "polynom":   # industrial_poly without the tree (n_robust = 0: soft T_R constraint), +-0.5 % around the golden start
+            return x_p[:n], np.zeros((min(n, 8), 3)), None, None
+        return x_o[:n], u_o[:n], np.zeros((min(n, 32), 4)), None          # discrete DAE oscillating masses
     raise ValueError(cfg)
 
 
@@ -65,7 +81,8 @@ def config_nlp(cfg):
     from oracle.nlp import FlatNLP
     d = {1: lambda: models.oscillating_masses(10), 3: lambda: models.batch_reactor(30, 1), 4: lambda: models.dip(50),
          5: lambda: models.industrial_poly(20, 1), "kite": models.kite, "kinbike": models.kinematic_bicycle,
-         "dynbike": models.dynamic_bicycle}[cfg]()
+         "dynbike": models.dynamic_bicycle, "cstrrob": models.cstr_robust, "reactor": lambda: models.batch_reactor(20, 0),
+         "polynom": lambda: models.industrial_poly(20, 0), "oscdae": lambda: models.oscillating_masses_dae(7)}[cfg]()
     return FlatNLP(d)
 
 
@@ -96,7 +113,8 @@ def main():
     import multiprocessing as mp
     for cfg in a.cfgs:
         x0, up, z0, tvp = config_inputs(cfg, a.n)
-        jobs = [(cfg, i, x0[i], up[i], None if z0 is None else z0[i], tvp) for i in range(a.n)]
+        a_n = len(x0)                                         # some families define fewer instances than --n
+        jobs = [(cfg, i, x0[i], up[i], None if z0 is None else z0[i], tvp) for i in range(a_n)]
         t0 = time.perf_counter()
         with mp.get_context("fork").Pool(a.procs) as pool:
             res = pool.map(_work, jobs, chunksize=1)
@@ -108,7 +126,7 @@ def main():
         if tvp is not None: out["tvp"] = tvp
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"cfg{cfg}_oracle.npz"), **out)
         ok = (out["status"] == 0) | (out["status"] == 1)
-        print(f"cfg{cfg}: {a.n} instances in {time.perf_counter() - t0:.1f} s wall; success {ok.mean():.3f}; iterations mean "
+        print(f"cfg{cfg}: {a_n} instances in {time.perf_counter() - t0:.1f} s wall; success {ok.mean():.3f}; iterations mean "
               f"{out['iter_count'].mean():.1f} max {out['iter_count'].max()}; restorations {out['restorations'].sum()}; "
               f"status hist {dict(zip(*np.unique(out['status'], return_counts=True)))}", flush=True)
 

@@ -8,10 +8,11 @@ from conftest import HostSim
 from config_cases import MAX_ITER, compare_with_oracle, config_mpc, fixture
 
 CASES = {1: np.arange(64), 3: np.array([0, 1]), 4: np.array([0, 1, 2]), 5: np.array([0, 1, 2, 3]),
-         "kite": np.arange(32), "kinbike": np.arange(32), "dynbike": np.arange(32)}
+         "kite": np.arange(32), "kinbike": np.arange(32), "dynbike": np.arange(32),
+         "cstrrob": np.arange(16), "reactor": np.arange(16), "polynom": np.arange(8), "oscdae": np.arange(32)}
 
 
-@pytest.mark.parametrize("cfg", [1, 3, 4, 5, "kite", "kinbike", "dynbike"])
+@pytest.mark.parametrize("cfg", [1, 3, 4, 5, "kite", "kinbike", "dynbike", "cstrrob", "reactor", "polynom", "oscdae"])
 def test_config_matches_oracle_fixture(cfg):
     mpc = config_mpc(cfg, setup=False)
     fx = fixture(cfg)
