@@ -79,3 +79,33 @@ def test_integrator_order_and_substeps():
     e2 = np.abs(sim_step(lib, model, x, u, None, None, p, 0.005, n_sub=2)[0] - ref).max()
     e20 = np.abs(sim_step(lib, model, x, u, None, None, p, 0.005, n_sub=20)[0] - ref).max()
     assert e2 < e1 / 8 and e20 < 1e-10
+
+
+@pytest.mark.parametrize("name", ["kite", "kinematic_bicycle", "dynamic_bicycle"])
+def test_example_families_without_golden_against_an_independent_integrator(name):
+    """examples/kite, kinematic_bicycle_model, dynamic_bicycle_model ship no closed-loop golden: the generated integrator code
+    (tan / atan / atan2 / sqrt paths of the code generator) against scipy's DOP853 (rtol = atol = 1e-12) on the oracle's sympy
+    restatement of the same right-hand side, from 16 random states and inputs inside the examples' bounds."""
+    import sympy as sy
+    from scipy.integrate import solve_ivp
+    import bicycle, kite
+    from oracle import models
+    make, d, t_step, p = {"kite": (kite.kite_model, models.kite(), 0.15, [6.0, 10.0]),
+                          "kinematic_bicycle": (bicycle.kinematic_model, models.kinematic_bicycle(), 0.05, None),
+                          "dynamic_bicycle": (bicycle.dynamic_model, models.dynamic_bicycle(), 0.1, None)}[name]
+    model = make()
+    lib = build_simhost(model, name)
+    m = d.model
+    f = sy.lambdify([m.x, m.u, m.p], m.rhs, "numpy")
+    rng = np.random.RandomState(1)
+    lo = np.where(np.isfinite(d.x_lb), np.maximum(d.x_lb, -2.0), -2.0); hi = np.where(np.isfinite(d.x_ub), np.minimum(d.x_ub, 2.0), 2.0)
+    X = lo + (0.2 + 0.6 * rng.uniform(size=(16, m.n_x))) * (hi - lo)                  # inside 60 % of the (clipped) state box
+    U = d.u_lb + (0.3 + 0.4 * rng.uniform(size=(16, m.n_u))) * (d.u_ub - d.u_lb)
+    P = None if p is None else np.tile(p, (16, 1))
+    xn, _, st = sim_step(lib, model, X, U, None, None, P, t_step)
+    assert np.all(st == 0)
+    for b in range(16):
+        pv = [] if p is None else list(P[b])
+        sol = solve_ivp(lambda t, x: np.array(f(list(x), list(U[b]), pv), dtype=float), (0.0, t_step), X[b], method="DOP853", rtol=1e-12, atol=1e-12)
+        err = np.abs(xn[b] - sol.y[:, -1]) / (1.0 + np.abs(sol.y[:, -1]))
+        assert err.max() < 5e-8, (name, b, err.max())          # the bar of the golden families above
