@@ -724,7 +724,7 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     // ---- LU with partial pivoting; columns [NY, TILE_NC) ride along.  The diagonal keeps the RECIPROCAL pivot. ------
     // (measured and rejected, twice: the lane's row held in registers for the whole elimination, only the pivot row going
     //  through shared memory — one load per multiply-add instead of two loads and a store, but fully unrolled over the pivot
-    //  steps.  Round 2, cfg #2 on B200: 24.88 ms against 23.97 ms for this loop, identical iterates; gpurun_out/c1_reglu*.json)
+    //  steps.  Round 2, cfg #2 on B200: 24.88 ms against 23.97 ms for this loop, identical iterates; profiles/r2_reg_lu_ab.json)
     for (int k = 0; k < NY; ++k) {
       double best = -1.0; int myr = -1;
       if (act) for (int r = c.gl; r < NY; r += GSZ) if (r >= k) { const double a = fabs(T[r * TILE_LD + k]); if (a > best) { best = a; myr = r; } }
