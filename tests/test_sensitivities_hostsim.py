@@ -138,3 +138,40 @@ def test_model_parameter_columns_match_finite_differences():
         fd = (op["x"][0] - om["x"][0]) / (2 * h)
         scale = np.abs(fd[iu]).max()
         assert scale > 1e-5 and np.abs(dx[0, jc][iu] - fd[iu]).max() < 5e-2 * scale, (j, dx[0, jc][iu], fd[iu])
+
+
+@pytest.mark.parametrize("name", ["kite", "kinematic_bicycle", "dynamic_bicycle"])
+def test_example_families_without_golden(name):
+    """examples/kite (objective through a parameter-dependent aux expression: the columns of the uncertain parameters are not
+    trivial; soft constraint with a bounded slack), kinematic / dynamic bicycle: every opt_p column of dx*/dp against the
+    restated reference algorithm and, for the first input, against central differences of re-solved problems.  The multiplier
+    sensitivities are compared where they are unique (the dynamic bicycle ends with the yaw-rate bound active on node and
+    collocation copies of the same state: LICQ fails, the split of the bound multipliers is arbitrary while dx is not)."""
+    import bicycle, kite
+    make, mo, x0, up = {"kite": (lambda: kite.kite_mpc(setup=False), models.kite, np.array([0.5, 0.3, 0.2]), np.zeros(1)),
+                        "kinematic_bicycle": (lambda: bicycle.kinematic_mpc(setup=False), models.kinematic_bicycle, np.array([0.2, -0.3, 0.1, 0.5]), np.zeros(2)),
+                        "dynamic_bicycle": (lambda: bicycle.dynamic_mpc(setup=False), models.dynamic_bicycle, np.array([0.0, 0.2, 0.05, 1.0, 0.0, 0.0]), np.zeros(2))}[name]
+    mpc = make(); mpc.prepare_nlp(); r = mpc.recipe
+    sim = HostSim(mpc, "sens_" + name); sim.o.max_iter = 300
+    P, x0s, u0s, z0s = mpc.pack_batch(x0[None], up[None], None)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    assert out["status"][0] == 0
+    dx, dl, sst = sim.sens(out["x"], out["lam_g"], P, want_dlam=True)
+    assert sst[0] == 0
+    nlp = FlatNLP(mo())
+    dxo, dlo = nlp_sensitivity(nlp, out["x"][0], out["lam_g"][0], P[0], nlp.lbx, nlp.ubx, nlp.lbg, nlp.ubg)
+    assert np.abs(dx[0].T - dxo).max() < 1e-6 * max(1.0, np.abs(dxo).max())
+    if name != "dynamic_bicycle":
+        assert np.abs(dl[0].T - dlo).max() < 1e-6 * max(1.0, np.abs(dlo).max())
+    iu = np.asarray(mpc._opt_x.f_index(("_u", 0, 0)), dtype=int)
+    seen = 0.0
+    for j in range(r.n_p):
+        h = 1e-5 * max(1.0, abs(P[0, j]))
+        Pp = P.copy(); Pp[0, j] += h
+        Pm = P.copy(); Pm[0, j] -= h
+        op = sim.solve(Pp, x_init=out["x"]); om = sim.solve(Pm, x_init=out["x"])
+        assert op["status"][0] == 0 and om["status"][0] == 0
+        fd = (op["x"][0] - om["x"][0]) / (2 * h)
+        assert np.abs(dx[0, j][iu] - fd[iu]).max() < 5e-4 * max(1.0, np.abs(fd[iu]).max()), (name, j)
+        seen = max(seen, np.abs(fd[iu]).max())
+    assert seen > 0.05
