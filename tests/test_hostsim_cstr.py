@@ -70,3 +70,19 @@ def test_matches_oracle_iterates(sim, dataset):
             used = nlp.used_mask()
             assert np.abs(r["x"][used] - out["x"][b][used]).max() < 1e-8
             assert np.abs(r["lam_g"] - out["lam_g"][b]).max() < 1e-6 * max(1.0, np.abs(r["lam_g"]).max())
+
+
+def test_pathological_inputs_terminate_with_a_failure_status():
+    """NaN / Inf / absurd initial states must end the solve at once with a failure status (the reference does not raise either,
+    optimizer.py:770-778: only `success` is False) — on the device a solve that never ends would take the whole batch with it."""
+    import cstr
+    from conftest import HostSim
+    mpc = cstr.cstr_nominal_mpc(setup=False); mpc.prepare_nlp()
+    sim = HostSim(mpc, "cstr_nom"); sim.o.max_iter = 300
+    x0 = np.array([0.8, 0.5, 134.14, 130.0]); up = np.array([5.0, -1000.0])
+    X = np.stack([np.where(np.arange(4) == 0, np.nan, x0), np.where(np.arange(4) == 1, np.inf, x0), x0 * 1e12, -10 * x0, 0 * x0, x0])
+    P, x0s, u0s, z0s = mpc.pack_batch(X, np.repeat(up[None, :], len(X), axis=0), None)
+    out = sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s)
+    assert np.all(out["iter_count"] <= 300)
+    assert not out["success"][:5].any() and out["success"][5]                 # the sane instance in the same batch still converges
+    assert np.all(np.isin(out["status"][:2], (-3, -13)))                      # NaN / Inf: step computation fails / invalid number
