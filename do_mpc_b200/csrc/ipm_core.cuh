@@ -728,7 +728,8 @@ DMB_PHASE void factor_edges(const Ctx& c, const Inst& I, const double* res, doub
     for (int k = 0; k < NY; ++k) {
       double best = -1.0; int myr = -1;
       if (act) for (int r = c.gl; r < NY; r += GSZ) if (r >= k) { const double a = fabs(T[r * TILE_LD + k]); if (a > best) { best = a; myr = r; } }
-      const int pr = group_argmax(c, best, myr);
+      int pr = group_argmax(c, best, myr);
+      if (pr < k || pr >= NY) pr = k;        // a column of NaNs has no candidate: keep row k (the pivot test below fails the step)
       if (act && pr != k) {
         for (int cc = c.gl; cc < TILE_NC; cc += GSZ) {
           const double t = T[k * TILE_LD + cc]; T[k * TILE_LD + cc] = T[pr * TILE_LD + cc]; T[pr * TILE_LD + cc] = t;
