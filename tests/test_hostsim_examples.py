@@ -66,3 +66,35 @@ def test_industrial_poly_with_and_without_iterative_refinement():
     # (before the Riccati updates were made exactly symmetric this run ended with status -2 at the round-off floor; it now
     #  converges as well — the refinement stays on by default like IPOPT's)
     assert np.abs(out0["u0_scaled"][0] - g["u"][0] / r.u_scaling).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["cstr_robust", "dip50", "kite", "reactor_tree", "osc_dae"])
+def test_pathological_instances_fail_fast_and_leave_the_next_instance_alone(name):
+    """A batch that mixes NaN / Inf / absurd initial states with a sane one (scenario tree, DAE + hard constraints, soft constraint,
+    discrete DAE): the bad instances end with a failure status within the iteration limit, the sane instance that the same CTA
+    solves afterwards converges exactly as it does alone.  (The reference never raises for a failed solve either,
+    optimizer.py:770-778.)  Run twice: an out-of-tile access shows up as a changing outcome (and under AddressSanitizer with
+    DMB_HOSTSIM_FLAGS=-fsanitize=address, LD_PRELOAD=libasan.so: clean for the whole CPU suite)."""
+    import batch_reactor, cstr, dip, kite, oscillating_masses
+    from conftest import GOLDEN
+    make, x0, up, z0, tvp = {
+        "cstr_robust": (lambda: cstr.cstr_robust_mpc(setup=False), np.load(GOLDEN / "kkt_CSTR.npz")["x"][0], np.zeros(2), None, None),
+        "dip50": (lambda: dip.dip_mpc(n_horizon=50, setup=False), np.array([0.0, 2.8, 2.8, 0, 0, 0]), np.zeros(1), np.zeros(3), np.full((51, 1), -0.8)),
+        "kite": (lambda: kite.kite_mpc(setup=False), np.array([0.5, 0.3, 0.2]), np.zeros(1), None, None),
+        "reactor_tree": (lambda: batch_reactor.reactor_mpc(n_horizon=10, n_robust=1, setup=False), np.array([1.0, 0.5, 0.0, 120.0]), np.zeros(1), None, None),
+        "osc_dae": (lambda: oscillating_masses.osc_dae_mpc(setup=False), np.array([0.5, -0.5, 0.2, 0.1]), np.zeros(1), np.zeros(4), None)}[name]
+    mpc = make(); mpc.prepare_nlp()
+    sim = HostSim(mpc, "patho_" + name); sim.o.max_iter = 100
+    n = len(x0)
+    X = np.stack([np.where(np.arange(n) == 0, np.nan, x0), np.where(np.arange(n) == n - 1, np.inf, x0), x0 * 1e12, np.full(n, np.nan), x0])
+    B = len(X)
+    kw = {} if tvp is None else {"tvp": tvp}
+    P, x0s, u0s, z0s = mpc.pack_batch(X, np.repeat(up[None], B, axis=0), None if z0 is None else np.repeat(z0[None], B, axis=0), **kw)
+    alone = sim.solve(P[-1:], x0s=x0s[-1:], u0s=u0s[-1:], z0s=None if z0s is None else z0s[-1:])
+    assert alone["status"][0] == 0
+    outs = [sim.solve(P, x0s=x0s, u0s=u0s, z0s=z0s) for _ in range(2)]
+    for out in outs:
+        assert not out["success"][:4].any() and np.all(out["iter_count"] <= 100)
+        assert out["status"][-1] == 0 and out["iter_count"][-1] == alone["iter_count"][0]
+        assert np.array_equal(out["u0_scaled"][-1], alone["u0_scaled"][0])
+    assert np.array_equal(outs[0]["status"], outs[1]["status"]) and np.array_equal(outs[0]["iter_count"], outs[1]["iter_count"])
